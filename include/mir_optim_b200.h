@@ -212,6 +212,10 @@ uint64_t    mir_b200_kernel_launches(void);
 /* Number of visible CUDA devices (0 when there is none; never fails). */
 int         mir_b200_device_count(void);
 const char* mir_b200_version(void);
+/* Roofline denominators not in MEASURED_PEAKS.json, measured on the current device:
+ * kind 0 = FP64 FMA pipe, 1 = FP64 tensor (mma.sync m8n8k4 f64 -> DMMA), 2 = FP32 FMA pipe.
+ * Returns TFLOP/s (best of `reps` launches) or a negative mir_b200_error. */
+double      mir_b200_measure_peak_tflops(int kind, int reps);
 
 /*
  * Device residual models ("device functors").  r = residual vector (length m), p = parameters

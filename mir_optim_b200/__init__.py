@@ -1,0 +1,45 @@
+"""mir_optim_b200 -- B200-native Levenberg-Marquardt / BOXCQP engine behind mir-optim's API.
+
+The compute lives in ``libmir_optim_b200.so`` (hand-written sm_100a CUDA, C ABI declared in
+``include/mir_optim_b200.h``).  This package is only the host-side mirror of the reference's
+operator interface; it never computes and has no CPU fallback: importing it without the built
+library raises, and calling it without a CUDA device returns the library's error.
+"""
+from __future__ import annotations
+
+import ctypes as _C
+import os as _os
+
+from . import _abi
+from ._abi import (BoxQPStatus, LeastSquaresStatus, ModelDesc, ModelId, BatchStats,  # noqa: F401
+                   MODEL_FD_JACOBIAN, MODEL_GRID_PER_PROBLEM)
+
+_HERE = _os.path.dirname(_os.path.abspath(__file__))
+LIB_PATH = _os.path.join(_HERE, "libmir_optim_b200.so")
+
+
+class LibraryMissing(ImportError):
+    pass
+
+
+def load_library(path: str = LIB_PATH):
+    if not _os.path.exists(path):
+        raise LibraryMissing(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C mir_optim_b200/csrc`).  There is no CPU fallback.")
+    lib = _C.CDLL(path, mode=_C.RTLD_LOCAL)
+    _abi.bind_reference_abi(lib)
+    _abi.bind_b200_abi(lib)
+    return lib
+
+
+lib = load_library()
+
+from .api import ReferenceAPI, LeastSquaresException  # noqa: E402
+from .engine import Engine, B200Error, RESULT_DTYPES  # noqa: E402
+
+engine = Engine(lib)
+
+__all__ = ["lib", "engine", "Engine", "B200Error", "ReferenceAPI", "LeastSquaresException", "LeastSquaresStatus",
+           "BoxQPStatus", "ModelId", "ModelDesc", "BatchStats", "MODEL_FD_JACOBIAN", "MODEL_GRID_PER_PROBLEM",
+           "RESULT_DTYPES", "LIB_PATH"]

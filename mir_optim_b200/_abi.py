@@ -127,6 +127,7 @@ REFERENCE_SYMBOLS = [
 
 B200_SYMBOLS = [
     "mir_b200_last_error", "mir_b200_kernel_launches", "mir_b200_device_count", "mir_b200_version",
+    "mir_b200_measure_peak_tflops",
     "mir_b200_device_model_d", "mir_b200_device_model_jac_d", "mir_b200_device_model_s", "mir_b200_device_model_jac_s",
     "mir_optimize_least_squares_batched_d", "mir_optimize_least_squares_batched_s",
     "mir_optimize_least_squares_batched_dev_d", "mir_optimize_least_squares_batched_dev_s",
@@ -164,6 +165,7 @@ def bind_b200_abi(lib):
     lib.mir_b200_kernel_launches.argtypes = []; lib.mir_b200_kernel_launches.restype = C.c_uint64
     lib.mir_b200_device_count.argtypes = []; lib.mir_b200_device_count.restype = C.c_int
     lib.mir_b200_version.argtypes = []; lib.mir_b200_version.restype = C.c_char_p
+    lib.mir_b200_measure_peak_tflops.argtypes = [C.c_int, C.c_int]; lib.mir_b200_measure_peak_tflops.restype = C.c_double
     vp = C.c_void_p
     for sfx, S, R, Q in (("d", LeastSquaresSettingsD, LeastSquaresResultD, BoxQPSettingsD),
                          ("s", LeastSquaresSettingsS, LeastSquaresResultS, BoxQPSettingsS)):

@@ -1,0 +1,123 @@
+// lm_batched.cu -- C ABI of the batched LM entry points (header part 2): argument checks,
+// staging of host buffers, stream-ordered scratch, launch of the warp-per-problem kernel.
+#include <cstring>
+#include <string>
+
+#include "lm_small_launch.cuh"
+#include "runtime.cuh"
+
+namespace mirb200 {
+
+template <class T>
+static int batched_dev(const typename Num<T>::Settings* settings, const mir_model_desc* model, size_t batch, size_t m, size_t n,
+                       T* x, const T* l, const T* u, size_t bound_stride, typename Num<T>::Result* results,
+                       mir_batch_stats* stats, cudaStream_t stream)
+{
+    clear_error();
+    if (!settings || !model || (batch && (!x || !l || !u || !results))) { set_error("mir_optim_b200: null argument"); return MIR_B200_EINVAL; }
+    if (n == 0) { set_error("mir_optim_b200: n must be > 0 for the batched entry point"); return MIR_B200_EINVAL; }
+    if (bound_stride != 0 && bound_stride < n) { set_error("mir_optim_b200: bound_stride must be 0 or >= n"); return MIR_B200_EINVAL; }
+    if (batch == 0) return MIR_B200_OK;
+    int rc = require_device(-1);
+    if (rc) return rc;
+
+    unsigned long long* counter = nullptr;
+    MIRB200_CUDA(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), stream));
+    MIRB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+
+    SmallBatchArgs a;
+    a.t = model->t; a.y = model->y; a.x = x; a.l = l; a.u = u; a.results = results;
+    a.counter = counter; a.stats = stats; a.batch = batch; a.m = (unsigned)m;
+    a.bound_stride = (unsigned)bound_stride; a.flags = model->flags;
+    rc = launch_small_model<T>(model->model, n, *settings, a, stream);
+    cudaFreeAsync(counter, stream);
+    return rc;
+}
+
+template <class T>
+static int batched_host(const typename Num<T>::Settings* settings, const mir_model_desc* model, size_t batch, size_t m, size_t n,
+                        T* x, const T* l, const T* u, size_t bound_stride, typename Num<T>::Result* results,
+                        mir_batch_stats* stats, int device)
+{
+    using Result = typename Num<T>::Result;
+    clear_error();
+    if (!settings || !model || (batch && (!x || !l || !u || !results))) { set_error("mir_optim_b200: null argument"); return MIR_B200_EINVAL; }
+    int rc = require_device(device);
+    if (rc) return rc;
+    if (batch == 0) return MIR_B200_OK;
+
+    const bool per = (model->flags & MIR_MODEL_GRID_PER_PROBLEM) != 0;
+    const size_t tBytes = model->t ? sizeof(T) * (per ? batch * m : m) : 0;
+    const size_t yBytes = model->y ? sizeof(T) * batch * m : 0;
+    const size_t xBytes = sizeof(T) * batch * n;
+    const size_t bBytes = sizeof(T) * (bound_stride ? batch * bound_stride : n);
+    const size_t rBytes = sizeof(Result) * batch;
+
+    cudaStream_t stream = nullptr;
+    MIRB200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t total = align(tBytes) + align(yBytes) + align(xBytes) + 2 * align(bBytes) + align(rBytes) + align(sizeof(mir_batch_stats));
+    char* base = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&base, total, stream);
+    if (e != cudaSuccess) { cudaStreamDestroy(stream); return check_cuda(e, "cudaMallocAsync(batch buffers)"); }
+    char* p = base;
+    T* dt = (T*)p; p += align(tBytes);
+    T* dy = (T*)p; p += align(yBytes);
+    T* dx = (T*)p; p += align(xBytes);
+    T* dl = (T*)p; p += align(bBytes);
+    T* du = (T*)p; p += align(bBytes);
+    Result* dr = (Result*)p; p += align(rBytes);
+    mir_batch_stats* ds = (mir_batch_stats*)p;
+
+    rc = MIR_B200_OK;
+    auto CK = [&](cudaError_t err, const char* what) { if (rc == MIR_B200_OK) rc = check_cuda(err, what); };
+    if (tBytes) CK(cudaMemcpyAsync(dt, model->t, tBytes, cudaMemcpyHostToDevice, stream), "H2D t");
+    if (yBytes) CK(cudaMemcpyAsync(dy, model->y, yBytes, cudaMemcpyHostToDevice, stream), "H2D y");
+    CK(cudaMemcpyAsync(dx, x, xBytes, cudaMemcpyHostToDevice, stream), "H2D x");
+    CK(cudaMemcpyAsync(dl, l, bBytes, cudaMemcpyHostToDevice, stream), "H2D l");
+    CK(cudaMemcpyAsync(du, u, bBytes, cudaMemcpyHostToDevice, stream), "H2D u");
+    if (stats) CK(cudaMemsetAsync(ds, 0, sizeof(mir_batch_stats), stream), "memset stats");
+    if (rc == MIR_B200_OK) {
+        mir_model_desc dm = *model;
+        dm.t = tBytes ? dt : nullptr; dm.y = yBytes ? dy : nullptr;
+        rc = batched_dev<T>(settings, &dm, batch, m, n, dx, dl, du, bound_stride, dr, stats ? ds : nullptr, stream);
+    }
+    if (rc == MIR_B200_OK) {
+        CK(cudaMemcpyAsync(x, dx, xBytes, cudaMemcpyDeviceToHost, stream), "D2H x");
+        CK(cudaMemcpyAsync(results, dr, rBytes, cudaMemcpyDeviceToHost, stream), "D2H results");
+        if (stats) CK(cudaMemcpyAsync(stats, ds, sizeof(mir_batch_stats), cudaMemcpyDeviceToHost, stream), "D2H stats");
+    }
+    cudaFreeAsync(base, stream);
+    cudaError_t se = cudaStreamSynchronize(stream);
+    if (rc == MIR_B200_OK) rc = check_cuda(se, "batched LM kernel");
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+}  // namespace mirb200
+
+using namespace mirb200;
+
+extern "C" {
+
+int mir_optimize_least_squares_batched_d(const mir_least_squares_settings_d* s, const mir_model_desc* model, size_t batch, size_t m,
+    size_t n, double* x, const double* l, const double* u, size_t bound_stride, mir_least_squares_result_d* results,
+    mir_batch_stats* stats, int device)
+{ return batched_host<double>(s, model, batch, m, n, x, l, u, bound_stride, results, stats, device); }
+
+int mir_optimize_least_squares_batched_s(const mir_least_squares_settings_s* s, const mir_model_desc* model, size_t batch, size_t m,
+    size_t n, float* x, const float* l, const float* u, size_t bound_stride, mir_least_squares_result_s* results,
+    mir_batch_stats* stats, int device)
+{ return batched_host<float>(s, model, batch, m, n, x, l, u, bound_stride, results, stats, device); }
+
+int mir_optimize_least_squares_batched_dev_d(const mir_least_squares_settings_d* s, const mir_model_desc* model, size_t batch, size_t m,
+    size_t n, double* x, const double* l, const double* u, size_t bound_stride, mir_least_squares_result_d* results,
+    mir_batch_stats* stats, void* stream)
+{ return batched_dev<double>(s, model, batch, m, n, x, l, u, bound_stride, results, stats, (cudaStream_t)stream); }
+
+int mir_optimize_least_squares_batched_dev_s(const mir_least_squares_settings_s* s, const mir_model_desc* model, size_t batch, size_t m,
+    size_t n, float* x, const float* l, const float* u, size_t bound_stride, mir_least_squares_result_s* results,
+    mir_batch_stats* stats, void* stream)
+{ return batched_dev<float>(s, model, batch, m, n, x, l, u, bound_stride, results, stats, (cudaStream_t)stream); }
+
+}  // extern "C"

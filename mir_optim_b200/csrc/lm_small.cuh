@@ -1,0 +1,383 @@
+// lm_small.cuh -- one group (LANES lanes of a warp; LANES = 32 is "one warp per problem") per
+// Levenberg-Marquardt problem.  Persistent groups pull problem indices from an atomic counter.
+//
+// Follows optimizeLeastSquaresImplGeneric!T, least_squares.d:877-1176 (line cites inline).
+//
+// Data layout.  Residual rows are dealt round-robin to the lanes (row = k*LANES + lane, k < R):
+// each lane keeps its rows of y (current residuals), mBuffer (trial / previous residuals), the
+// abscissa/observations and its rows of J in registers, so J (needed in place by the Broyden
+// update, LS:1003-1006) never leaves the register file.  The n-sized state (x, bounds, J^T r,
+// packed lower J^T J, lambda, mu, age, counters) is replicated bit-identically in every lane:
+// all cross-row reductions are xor-butterflies, which hand every lane the same bits, so the
+// "serial" part (BoxQP / Cholesky / lambda control) needs no communication and no divergence.
+//
+// Equivalences used (all bit-exact with respect to this file's own arithmetic):
+//   * J^T J is rebuilt only when J changed (the reference re-runs syrk every pass, LS:1065; with
+//     unchanged J it returns the same matrix).
+//   * If the trial point equals x bit for bit, f(trial) == y and trial residual == residual, so
+//     the pass is a rejection (LS:1124-1130); the model evaluation is skipped, fCalls still counts it.
+#pragma once
+#include "boxqp_small.cuh"
+#include "models.cuh"
+
+namespace mirb200 {
+
+struct SmallBatchArgs {
+    const void* t;          // abscissa: T[m] or T[batch*m]
+    const void* y;          // observations T[batch*m]
+    void*       x;          // T[batch*n] in/out
+    const void* l;          // T[n] or T[batch*bound_stride]
+    const void* u;
+    void*       results;    // Result[batch]
+    unsigned long long* counter;   // work queue head (zeroed by the launcher)
+    mir_batch_stats* stats; // may be null
+    unsigned long long batch;
+    unsigned m;
+    unsigned bound_stride;
+    unsigned flags;         // MIR_MODEL_* flags
+};
+
+template <class Model, class T, int LANES, int R>
+__global__ void __launch_bounds__(128)
+lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
+{
+    constexpr int N = Model::N;
+    constexpr int NP = N * (N + 1) / 2;
+    using Result = typename Num<T>::Result;
+
+    const unsigned gmask = group_mask<LANES>();
+    const int glane = threadIdx.x & (LANES - 1);
+    const int m = (int)args.m;
+    const bool useFD = (args.flags & MIR_MODEL_FD_JACOBIAN) != 0;
+    const bool gridPerProblem = (args.flags & MIR_MODEL_GRID_PER_PROBLEM) != 0;
+    const T* __restrict__ tptr = static_cast<const T*>(args.t);
+    const T* __restrict__ yptr = static_cast<const T*>(args.y);
+
+    // local work counters, flushed once per group at the end
+    unsigned long long sPasses = 0, sAccepted = 0, sFresh = 0, sBroyden = 0, sEvals = 0, sSolves = 0, sQPIt = 0, sProblems = 0;
+
+    // abscissa shared by every problem: load once
+    T tt[R];
+    if (Model::kHasData && !gridPerProblem) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) { const int row = k * LANES + glane; tt[k] = row < m ? tptr[row] : (T)0; }
+    }
+
+    for (;;) {
+        unsigned long long prob = 0;
+        if (glane == 0) prob = atomicAdd(args.counter, 1ull);
+        prob = __shfl_sync(gmask, prob, 0, LANES);
+        if (prob >= args.batch) break;
+        ++sProblems;
+
+        // ---- load the problem ----
+        T x[N], lo[N], up[N];
+        {
+            const T* xp = static_cast<const T*>(args.x) + prob * N;
+            const T* lp = static_cast<const T*>(args.l) + prob * args.bound_stride;
+            const T* upp = static_cast<const T*>(args.u) + prob * args.bound_stride;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { x[i] = xp[i]; lo[i] = lp[i]; up[i] = upp[i]; }
+        }
+        T yo[R];
+        if (Model::kHasData) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int row = k * LANES + glane;
+                yo[k] = row < m ? yptr[prob * (unsigned long long)m + row] : (T)0;
+                if (gridPerProblem) tt[k] = row < m ? tptr[prob * (unsigned long long)m + row] : (T)0;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) { yo[k] = (T)0; tt[k] = (T)0; }
+        }
+
+        Result ret;                                                   // LeastSquaresResult.init, LS:131-142
+        ret.status = mir_ls_numericError; ret.iterations = 0; ret.fCalls = 0; ret.gCalls = 0;
+        ret.residual = Num<T>::inf(); ret.lambda = (T)0;
+
+        // residual vector evaluation: out[k] = r_row(p) for this lane's rows, returns ||r||^2
+        auto eval = [&](const T (&p)[N], T (&out)[R]) -> T {
+            const typename Model::Pre pre = Model::prepare(p);
+            T part = (T)0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int row = k * LANES + glane;
+                T r = (T)0;
+                if (row < m) r = Model::residual(pre, p, row, tt[k], yo[k]);
+                out[k] = r;
+                part += r * r;
+            }
+            ++sEvals;
+            return group_sum<LANES>(gmask, part);
+        };
+
+        // ---- validation, LS:930-943 (first failure wins) ----
+        bool valid = false;
+        {
+            bool finite = true, inb = true;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                finite = finite && (-Num<T>::inf() < x[i] && x[i] < Num<T>::inf());
+                inb = inb && (lo[i] <= x[i]) && (x[i] <= up[i]);
+            }
+            if (m == 0 || !finite) ret.status = mir_ls_badGuess;
+            else if (!inb) ret.status = mir_ls_badBounds;
+            else if (!((T)0 <= st.minStepQuality && st.minStepQuality < (T)1)) ret.status = mir_ls_badMinStepQuality;
+            else if (!((T)0 <= st.goodStepQuality && st.goodStepQuality <= (T)1)) ret.status = mir_ls_badGoodStepQuality;
+            else if (!(st.minStepQuality < st.goodStepQuality)) ret.status = mir_ls_badStepQuality;
+            else if (!((T)1 <= st.lambdaIncrease && st.lambdaIncrease <= Num<T>::sqrt_max())) ret.status = mir_ls_badLambdaParams;
+            else if (!(Num<T>::sqrt_min_normal() <= st.lambdaDecrease && st.lambdaDecrease <= (T)1)) ret.status = mir_ls_badLambdaParams;
+            else valid = true;
+        }
+
+        if (valid) {
+            const unsigned maxAge = st.maxAge ? st.maxAge : (useFD ? 2u * N : 3u);          // LS:945
+
+            T yv[R], mb[R];          // y and mBuffer (this lane's rows)
+            T J[R][N];
+            T JJ[NP], Jy[N], dX[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { Jy[i] = (T)0; dX[i] = (T)0; }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) JJ[i] = (T)0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                mb[k] = (T)0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) J[k][i] = (T)0;
+            }
+
+            ret.residual = eval(x, yv);                                                      // LS:953-955
+            ret.fCalls = 1;
+            bool fConverged = ret.residual <= st.maxGoodResidual;                            // LS:956
+            bool needJacobian = true;                                                        // LS:959-971
+            bool jjDirty = true;
+            unsigned age = maxAge;
+            T lambda = (T)0, mu = (T)1, deltaX_dot = (T)0;
+            int status = mir_ls_maxIterations;
+            unsigned iterations = 0;
+
+            do {                                                                             // LS:972
+                ++sPasses;
+                if (fConverged) { status = mir_ls_fConverged; break; }                       // LS:974-978
+                if (!(lambda <= st.maxLambda)) { status = mir_ls_furtherImprovement; break; } // LS:979-983
+                if (mu > (T)16 && age) { needJacobian = true; age = maxAge; mu = (T)1; }     // LS:984-989
+                {
+                    bool nan = false;                                                        // LS:990-995
+#pragma unroll
+                    for (int i = 0; i < N; ++i) nan = nan || !(x[i] <= x[i]);
+                    if (nan) { status = mir_ls_numericError; break; }
+                }
+                if (needJacobian) {                                                          // LS:996
+                    needJacobian = false;
+                    jjDirty = true;
+                    if (age < maxAge) {                                                      // Broyden, LS:999-1007
+                        ++age; ++sBroyden;
+                        const T d = (T)1 / deltaX_dot;
+#pragma unroll
+                        for (int k = 0; k < R; ++k) {
+                            T v = mb[k] - yv[k];                                             // axpy(-1, y, mBuffer)
+                            T acc = (T)0;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) acc += J[k][i] * dX[i];              // gemv(1, J, deltaX, 1, mBuffer)
+                            v = (v + acc) * -d;                                              // scal(-d, mBuffer)
+                            mb[k] = v;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) J[k][i] += v * dX[i];                // ger(1, mBuffer, deltaX, J)
+                        }
+                    } else {
+                        age = 0; ++sFresh;                                                   // LS:1010
+                        if (!useFD) {                                                        // LS:1011-1015
+                            const typename Model::Pre pre = Model::prepare(x);
+#pragma unroll
+                            for (int k = 0; k < R; ++k) {
+                                const int row = k * LANES + glane;
+                                if (row < m) Model::jacobian(pre, x, row, tt[k], J[k]);
+                            }
+                            ret.gCalls += 1;
+                        } else {                                                             // LS:1018-1049
+#pragma unroll
+                            for (int j = 0; j < N; ++j) {
+                                T p[N];
+#pragma unroll
+                                for (int i = 0; i < N; ++i) p[i] = x[i];
+                                const T save = x[j];
+                                T xmh = save - st.jacobianEpsilon;
+                                T xph = save + st.jacobianEpsilon;
+                                xmh = t_max(xmh, lo[j]);
+                                xph = t_min(xph, up[j]);
+                                const T twh = xph - xmh;
+                                if (twh != (T)0) {
+                                    T fp[R], fm[R];
+                                    p[j] = xph; eval(p, fp);
+                                    p[j] = xmh; eval(p, fm);
+                                    const T rt = (T)1 / twh;
+#pragma unroll
+                                    for (int k = 0; k < R; ++k) J[k][j] = (fp[k] - fm[k]) * rt;
+                                    // (the reference evaluates through mBuffer, LS:1036-1039; nothing reads it
+                                    //  before the next trial evaluation overwrites it, so it is not mirrored)
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < R; ++k) J[k][j] = (T)0;
+                                }
+                            }
+                            ret.fCalls += N;                                                 // LS:1049 (counts tasks)
+                        }
+                    }
+                    {   // Jy = J^T y, LS:1052
+                        T part[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) part[i] = (T)0;
+#pragma unroll
+                        for (int k = 0; k < R; ++k)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) part[i] += J[k][i] * yv[k];
+                        group_sum_array<LANES, N>(gmask, part);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) Jy[i] = part[i];
+                    }
+                    T gmax = (T)0; bool gnan = false;                                        // LS:1053
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { gmax = t_max(gmax, t_abs(Jy[i])); gnan = gnan || !(Jy[i] == Jy[i]); }
+                    // iamax picks an index by |.|; a NaN entry makes the reference's comparison false as well
+                    // only when it is the selected entry -- treat any NaN as "not above tolerance" is NOT safe,
+                    // so mirror BLAS: NaN never wins iamax unless it is the first element.
+                    if (gnan && !(Jy[0] == Jy[0])) gmax = Jy[0];
+                    if (!(gmax > st.gradTolerance)) {                                        // LS:1053-1062
+                        if (age == 0) { status = mir_ls_gConverged; break; }
+                        age = maxAge;
+                        continue;
+                    }
+                }
+
+                if (jjDirty) {                                                               // syrk, LS:1065
+                    jjDirty = false;
+                    T part[NP];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) part[i] = (T)0;
+#pragma unroll
+                    for (int k = 0; k < R; ++k)
+#pragma unroll
+                        for (int i = 0; i < N; ++i)
+#pragma unroll
+                            for (int j = 0; j <= i; ++j) part[tri(i, j)] += J[k][i] * J[k][j];
+                    group_sum_array<LANES, NP>(gmask, part);
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) JJ[i] = part[i];
+                }
+
+                if (!(lambda >= st.minLambda)) {                                             // LS:1067-1072
+                    T dmax = JJ[0];                                                          // diag[iamax]: first max |.|; diag >= 0
+#pragma unroll
+                    for (int i = 1; i < N; ++i) if (t_abs(JJ[tri(i, i)]) > t_abs(dmax)) dmax = JJ[tri(i, i)];
+                    lambda = (T)(0.001 * (double)dmax);
+                    if (!(lambda >= st.minLambda)) lambda = (T)1;
+                }
+
+                T qpl[N], qpu[N];                                                            // LS:1074-1077
+#pragma unroll
+                for (int i = 0; i < N; ++i) { qpl[i] = lo[i] - x[i]; qpu[i] = up[i] - x[i]; }
+                QPCounters qc{0, 0};
+                const int qps = boxqp_small<T, N>(st.qpSettings, JJ, lambda, Jy, qpl, qpu, dX, qc);   // LS:1078-1080
+                sSolves += qc.solves; sQPIt += qc.iterations;
+                if (qps != mir_qp_solved) { status = mir_ls_numericError; break; }           // LS:1080-1085
+                {
+                    bool nan = false;                                                        // LS:1087-1092
+#pragma unroll
+                    for (int i = 0; i < N; ++i) nan = nan || !(dX[i] <= dX[i]);
+                    if (nan) { status = mir_ls_numericError; break; }
+                }
+                T nd = (T)0;                                                                 // LS:1096-1099
+#pragma unroll
+                for (int i = 0; i < N; ++i) { dX[i] = add_rn(add_rn(dX[i], x[i]), -x[i]); nd += dX[i] * dX[i]; }
+
+                if (!(t_sqrt(nd) < st.maxStep)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; continue; }   // LS:1101-1106
+
+                T xt[N];                                                                     // LS:1108-1110
+                bool same = true;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    xt[i] = t_max(t_min(add_rn(dX[i], x[i]), up[i]), lo[i]);
+                    same = same && (xt[i] == x[i]) && (signbit(xt[i]) == signbit(x[i]));
+                }
+                ++ret.fCalls;                                                                // LS:1112
+                T trial;
+                if (same) trial = ret.residual;         // f(xt) == y bit for bit: skip the evaluation
+                else      trial = eval(xt, mb);                                              // LS:1113-1115
+                if (!(trial <= Num<T>::inf())) { status = mir_ls_numericError; break; }      // LS:1117-1122
+
+                const T improvement = ret.residual - trial;                                  // LS:1124-1130
+                if (!(improvement > (T)0)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; continue; }
+
+                needJacobian = true; mu = (T)1; ++iterations; ++sAccepted;                   // LS:1132-1139
+#pragma unroll
+                for (int i = 0; i < N; ++i) x[i] = xt[i];
+#pragma unroll
+                for (int k = 0; k < R; ++k) { const T tmp = mb[k]; mb[k] = yv[k]; yv[k] = tmp; }
+                ret.residual = trial;
+                fConverged = ret.residual <= st.maxGoodResidual;
+                deltaX_dot = nd;
+
+                T pred = (T)0;                                                               // LS:1141-1142
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    T acc = (T)0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) acc += JJ[trisym(i, j)] * dX[j];
+                    Jy[i] = acc + (T)2 * Jy[i];          // symv(Lower, 1, JJ, deltaX, 2, Jy): Jy is scratch from here
+                    pred += Jy[i] * dX[i];
+                }
+                pred = -pred;
+                if (!(pred > (T)0)) { status = mir_ls_furtherImprovement; break; }           // LS:1144-1148
+
+                const T rho = pred / improvement;                                            // LS:1150
+                if (rho < st.minStepQuality) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; }   // LS:1152-1156
+                else if (rho >= st.goodStepQuality) lambda = t_max(st.lambdaDecrease * lambda * mu, st.minLambda);   // LS:1158-1161
+
+                // LS:1164: !(sqrt(dd) > absTol && nrm2(x) > sqrt(dd) * relTol)
+                T xmax = (T)0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) xmax = t_max(xmax, t_abs(x[i]));
+                T xn = (T)0;
+                if (xmax > (T)0) {
+                    const T inv = (T)1 / xmax;
+                    T ss = (T)0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { const T v = x[i] * inv; ss += v * v; }
+                    xn = xmax * t_sqrt(ss);
+                }
+                const T sd = t_sqrt(deltaX_dot);
+                if (!(sd > st.absTolerance && xn > sd * st.relTolerance)) {                  // LS:1164-1173
+                    if (age == 0) { status = mir_ls_xConverged; break; }
+                    age = maxAge;
+                    continue;
+                }
+            } while (iterations < st.maxIterations);                                         // LS:1175
+
+            ret.status = status;
+            ret.iterations = iterations;
+            ret.lambda = lambda;
+        }
+
+        if (glane == 0) {
+            T* xp = static_cast<T*>(args.x) + prob * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) xp[i] = x[i];
+            static_cast<Result*>(args.results)[prob] = ret;
+        }
+    }
+
+    if (args.stats && glane == 0 && sProblems) {
+        atomicAdd((unsigned long long*)&args.stats->problems, sProblems);
+        atomicAdd((unsigned long long*)&args.stats->passes, sPasses);
+        atomicAdd((unsigned long long*)&args.stats->accepted, sAccepted);
+        atomicAdd((unsigned long long*)&args.stats->fresh_jacobians, sFresh);
+        atomicAdd((unsigned long long*)&args.stats->broyden_updates, sBroyden);
+        atomicAdd((unsigned long long*)&args.stats->model_evals, sEvals);
+        atomicAdd((unsigned long long*)&args.stats->qp_solves, sSolves);
+        atomicAdd((unsigned long long*)&args.stats->qp_iterations, sQPIt);
+    }
+}
+
+}  // namespace mirb200

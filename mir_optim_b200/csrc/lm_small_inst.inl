@@ -1,0 +1,34 @@
+// lm_small_inst.inl -- model dispatch; included by lm_small_inst_d.cu / lm_small_inst_s.cu with REAL defined.
+#include <initializer_list>
+#include "lm_small_launch.cuh"
+
+namespace mirb200 {
+
+template <>
+int launch_small_model<REAL>(unsigned model, size_t n, const Num<REAL>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    using T = REAL;
+    auto bad_n = [&](int want) {
+        set_error("mir_optim_b200: model expects n = " + std::to_string(want) + ", got " + std::to_string(n));
+        return (int)MIR_B200_EINVAL;
+    };
+    switch (model) {
+    case MIR_MODEL_LINEAR2:    if (n != 2) return bad_n(2); return launch_small<ModelLinear2<T>, T, 32, 1>(st, args, stream);
+    case MIR_MODEL_ROSENBROCK: if (n != 2) return bad_n(2); return launch_small<ModelRosenbrock<T>, T, 32, 1>(st, args, stream);
+    case MIR_MODEL_SQRTCIRCLE: if (n != 2) return bad_n(2); return launch_small<ModelSqrtCircle<T>, T, 32, 1>(st, args, stream);
+    case MIR_MODEL_EXPDECAY2:  if (n != 2) return bad_n(2); return launch_small<ModelExpDecay2<T>, T, 32, 1, 4>(st, args, stream);
+    case MIR_MODEL_EXPTAU3:    if (n != 3) return bad_n(3); return launch_small<ModelExpTau3<T>, T, 32, 1, 4>(st, args, stream);
+    case MIR_MODEL_EXPDECAY3:  if (n != 3) return bad_n(3); return launch_small<ModelExpDecay3<T>, T, 32, 1, 4>(st, args, stream);
+    case MIR_MODEL_GAUSS4:     if (n != 4) return bad_n(4); return launch_small<ModelGauss4<T>, T, 32, 1, 2, 4>(st, args, stream);
+    case MIR_MODEL_SUMEXP:
+        if (n == 4) return launch_small<ModelSumExp<T, 4>, T, 32, 2, 4>(st, args, stream);
+        if (n == 8) return launch_small<ModelSumExp<T, 8>, T, 32, 2, 4>(st, args, stream);
+        set_error("mir_optim_b200: batched SUMEXP is instantiated for n = 4 and n = 8");
+        return MIR_B200_EUNSUPPORTED;
+    default:
+        set_error("mir_optim_b200: model id not available in the batched small-problem path");
+        return MIR_B200_EUNSUPPORTED;
+    }
+}
+
+}  // namespace mirb200

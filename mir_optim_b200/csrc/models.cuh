@@ -1,0 +1,125 @@
+// models.cuh -- device residual functors ("device functors" of the north star).
+//
+// A model supplies, for one residual row i with abscissa t_i and observation y_i,
+//     residual(pre, p, row, t, y)   = r_i(p)
+//     jacobian(pre, p, row, t, Jr)  = d r_i / d p_k, k < N     (row-major row of J, LS:154)
+// `prepare(p)` hoists per-parameter-vector work (reciprocals) out of the row loop.  These are
+// the GPU counterparts of the reference's LeastSquaresFunction / LeastSquaresJacobian
+// callbacks (least_squares.d:73-80); the first five are the reference's own unit-test
+// problems (least_squares.d:217-434).
+#pragma once
+#include "common.cuh"
+
+namespace mirb200 {
+
+template <class T> struct NoPre {};
+
+// r = (p0, 2 - p1)                                            least_squares.d:230-241
+template <class T> struct ModelLinear2 {
+    static constexpr int N = 2; static constexpr bool kHasData = false;
+    using Pre = NoPre<T>;
+    __device__ static Pre prepare(const T (&)[N]) { return {}; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int row, T, T) { return row == 0 ? p[0] : (T)2 - p[1]; }
+    __device__ static void jacobian(const Pre&, const T (&)[N], int row, T, T (&J)[N]) {
+        J[0] = row == 0 ? (T)1 : (T)0; J[1] = row == 0 ? (T)0 : (T)-1;
+    }
+};
+
+// Rosenbrock: r = (10 (p1 - p0^2), 1 - p0)                     least_squares.d:261-265, 295-301
+template <class T> struct ModelRosenbrock {
+    static constexpr int N = 2; static constexpr bool kHasData = false;
+    using Pre = NoPre<T>;
+    __device__ static Pre prepare(const T (&)[N]) { return {}; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int row, T, T) {
+        return row == 0 ? (T)10 * (p[1] - p[0] * p[0]) : (T)1 - p[0];
+    }
+    __device__ static void jacobian(const Pre&, const T (&p)[N], int row, T, T (&J)[N]) {
+        J[0] = row == 0 ? (T)-20 * p[0] : (T)-1; J[1] = row == 0 ? (T)10 : (T)0;
+    }
+};
+
+// r = sqrt(1 - (p0^2 + p1^2)), m = 1 < n = 2                   least_squares.d:427-430
+template <class T> struct ModelSqrtCircle {
+    static constexpr int N = 2; static constexpr bool kHasData = false;
+    using Pre = NoPre<T>;
+    __device__ static Pre prepare(const T (&)[N]) { return {}; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T, T) { return t_sqrt((T)1 - (p[0] * p[0] + p[1] * p[1])); }
+    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T, T (&J)[N]) {
+        T s = t_sqrt((T)1 - (p[0] * p[0] + p[1] * p[1]));
+        J[0] = -p[0] / s; J[1] = -p[1] / s;
+    }
+};
+
+// r_i = p0 exp(-t_i p1) - y_i                                  least_squares.d:347, 360
+template <class T> struct ModelExpDecay2 {
+    static constexpr int N = 2; static constexpr bool kHasData = true;
+    using Pre = NoPre<T>;
+    __device__ static Pre prepare(const T (&)[N]) { return {}; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) { return p[0] * t_exp(-t * p[1]) - y; }
+    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
+        T e = t_exp(-t * p[1]); J[0] = e; J[1] = -(p[0] * t) * e;
+    }
+};
+
+// r_i = p0 exp(-t_i / p1) + p2 - y_i                           least_squares.d:378, 390
+template <class T> struct ModelExpTau3 {
+    static constexpr int N = 3; static constexpr bool kHasData = true;
+    using Pre = NoPre<T>;
+    __device__ static Pre prepare(const T (&)[N]) { return {}; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) { return p[0] * t_exp(-t / p[1]) + p[2] - y; }
+    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
+        T e = t_exp(-t / p[1]); J[0] = e; J[1] = p[0] * e * t / (p[1] * p[1]); J[2] = (T)1;
+    }
+};
+
+// r_i = p0 exp(-p1 t_i) + p2 - y_i                             BASELINE configs[0]
+template <class T> struct ModelExpDecay3 {
+    static constexpr int N = 3; static constexpr bool kHasData = true;
+    using Pre = NoPre<T>;
+    __device__ static Pre prepare(const T (&)[N]) { return {}; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) { return p[0] * t_exp(-p[1] * t) + p[2] - y; }
+    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
+        T e = t_exp(-p[1] * t); J[0] = e; J[1] = -(p[0] * t) * e; J[2] = (T)1;
+    }
+};
+
+// Gaussian peak on a baseline: r_i = A exp(-(t_i - mu)^2 / (2 sigma^2)) + c - y_i, p = (A, mu, sigma, c)
+//                                                             BASELINE configs[1]
+template <class T> struct ModelGauss4 {
+    static constexpr int N = 4; static constexpr bool kHasData = true;
+    struct Pre { T is; };
+    __device__ static Pre prepare(const T (&p)[N]) { return {(T)1 / p[2]}; }
+    __device__ static T residual(const Pre& q, const T (&p)[N], int, T t, T y) {
+        T z = (t - p[1]) * q.is;
+        return p[0] * t_exp((T)-0.5 * (z * z)) + p[3] - y;
+    }
+    __device__ static void jacobian(const Pre& q, const T (&p)[N], int, T t, T (&J)[N]) {
+        T z = (t - p[1]) * q.is;
+        T e = t_exp((T)-0.5 * (z * z));
+        T ae = p[0] * e;
+        J[0] = e; J[1] = ae * z * q.is; J[2] = ae * (z * z) * q.is; J[3] = (T)1;
+    }
+};
+
+// Sum of exponentials: r_i = sum_k p[2k] exp(-p[2k+1] t_i) - y_i          BASELINE configs[2]
+template <class T, int N_> struct ModelSumExp {
+    static constexpr int N = N_; static constexpr bool kHasData = true;
+    static_assert(N_ % 2 == 0, "sum-of-exponentials has (amplitude, rate) pairs");
+    using Pre = NoPre<T>;
+    __device__ static Pre prepare(const T (&)[N]) { return {}; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
+        T acc = 0;
+#pragma unroll
+        for (int k = 0; k < N; k += 2) acc += p[k] * t_exp(-p[k + 1] * t);
+        return acc - y;
+    }
+    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+            T e = t_exp(-p[k + 1] * t);
+            J[k] = e; J[k + 1] = -(p[k] * t) * e;
+        }
+    }
+};
+
+}  // namespace mirb200

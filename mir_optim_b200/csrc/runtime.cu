@@ -1,0 +1,64 @@
+// runtime.cu -- process-wide helpers behind the C ABI (errors, launch counter, device queries).
+#include "runtime.cuh"
+
+#include <atomic>
+#include <cstring>
+
+namespace mirb200 {
+
+static thread_local std::string g_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const std::string& msg) { g_error = msg; }
+void clear_error() { g_error.clear(); }
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_cuda(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return MIR_B200_OK;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    cudaGetLastError();   // clear the sticky-less error state
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return MIR_B200_ENODEVICE;
+    return MIR_B200_ECUDA;
+}
+
+int require_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        set_error("mir_optim_b200: no usable CUDA device (this library has no CPU fallback): " +
+                  std::string(e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+        return MIR_B200_ENODEVICE;
+    }
+    if (device >= 0) {
+        if (device >= count) { set_error("mir_optim_b200: device index out of range"); return MIR_B200_EINVAL; }
+        return check_cuda(cudaSetDevice(device), "cudaSetDevice");
+    }
+    return MIR_B200_OK;
+}
+
+int sm_count()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
+
+}  // namespace mirb200
+
+extern "C" {
+
+const char* mir_b200_last_error(void) { return mirb200::g_error.c_str(); }
+uint64_t mir_b200_kernel_launches(void) { return mirb200::g_launches.load(); }
+int mir_b200_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+const char* mir_b200_version(void) { return "mir_optim_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""Batched / device-resident entry points (header part 2) with numpy and torch front ends.
+
+numpy arrays are HOST buffers: the library stages them to the GPU and back (the end-to-end
+path).  torch CUDA tensors are passed as device pointers to the ``*_dev`` entry points and are
+enqueued on torch's current stream (the resident path).  torch is plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import BatchStats, ModelDesc, ModelId, MODEL_FD_JACOBIAN, MODEL_GRID_PER_PROBLEM
+from .api import ReferenceAPI, _types
+
+RESULT_DTYPES = {
+    np.dtype(np.float64): np.dtype([("status", "<i4"), ("iterations", "<u4"), ("fCalls", "<u4"), ("gCalls", "<u4"),
+                                    ("residual", "<f8"), ("lambda", "<f8")]),
+    np.dtype(np.float32): np.dtype([("status", "<i4"), ("iterations", "<u4"), ("fCalls", "<u4"), ("gCalls", "<u4"),
+                                    ("residual", "<f4"), ("lambda", "<f4")]),
+}
+assert RESULT_DTYPES[np.dtype(np.float64)].itemsize == 32 and RESULT_DTYPES[np.dtype(np.float32)].itemsize == 24
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"mir_optim_b200 error {code}: {message}")
+        self.code = code
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())      # torch tensor
+
+
+class Engine(ReferenceAPI):
+    def __init__(self, lib):
+        super().__init__(lib)
+        _abi.bind_b200_abi(lib)
+
+    # -- helpers ----------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise B200Error(rc, self.lib.mir_b200_last_error().decode())
+
+    def device_count(self) -> int:
+        return self.lib.mir_b200_device_count()
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.mir_b200_kernel_launches())
+
+    # -- batched LM, host buffers -------------------------------------------------------
+    def optimize_batched(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
+                         t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
+                         fd_jacobian: bool = False, want_stats: bool = False, device: int = -1):
+        """Solve ``batch`` independent problems; x (batch, n) is updated in place.
+        l/u: shape (n,) shared, or (batch, n).  Returns (results structured array, stats dict | None)."""
+        sfx, real, S, R, *_ = _types(x.dtype)
+        assert isinstance(settings, S)
+        assert x.ndim == 2 and x.flags.c_contiguous
+        batch, n = x.shape
+        l = np.ascontiguousarray(l, dtype=x.dtype); u = np.ascontiguousarray(u, dtype=x.dtype)
+        bound_stride = 0 if l.ndim == 1 else n
+        flags = MODEL_FD_JACOBIAN if fd_jacobian else 0
+        if y is not None:
+            y = np.ascontiguousarray(y, dtype=x.dtype); assert y.shape[0] == batch
+            m = y.shape[1] if m is None else m
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=x.dtype)
+            if t.ndim == 2:
+                flags |= MODEL_GRID_PER_PROBLEM
+        assert m is not None, "m is required for data-free models"
+        desc = ModelDesc(int(model), flags, _vp(t), _vp(y))
+        results = np.empty(batch, dtype=RESULT_DTYPES[x.dtype])
+        stats = BatchStats() if want_stats else None
+        fn = getattr(self.lib, f"mir_optimize_least_squares_batched_{sfx}")
+        rc = fn(C.byref(settings), C.byref(desc), batch, m, n, _vp(x), _vp(l), _vp(u), bound_stride,
+                _vp(results), C.cast(C.pointer(stats), C.c_void_p) if stats is not None else None, device)
+        self._check(rc)
+        return results, (stats.as_dict() if stats is not None else None)
+
+    # -- batched LM, device-resident torch tensors ----------------------------------------
+    def optimize_batched_device(self, settings, model: ModelId, x, l, u, t=None, y=None, m: int | None = None,
+                                fd_jacobian: bool = False, results=None, stats=None, stream=None):
+        """All tensors are CUDA tensors on the current device; asynchronous on `stream` (default:
+        torch's current stream).  `results` : uint8 tensor (batch * sizeof(Result)); `stats`: int64[8] tensor."""
+        import torch
+        dt = np.dtype({torch.float64: np.float64, torch.float32: np.float32}[x.dtype])
+        sfx, real, S, R, *_ = _types(dt)
+        assert isinstance(settings, S) and x.is_cuda and x.is_contiguous()
+        batch, n = x.shape
+        bound_stride = 0 if l.dim() == 1 else n
+        flags = MODEL_FD_JACOBIAN if fd_jacobian else 0
+        if y is not None:
+            m = y.shape[1] if m is None else m
+        if t is not None and t.dim() == 2:
+            flags |= MODEL_GRID_PER_PROBLEM
+        if results is None:
+            results = torch.empty(batch * RESULT_DTYPES[dt].itemsize, dtype=torch.uint8, device=x.device)
+        desc = ModelDesc(int(model), flags, _vp(t), _vp(y))
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        fn = getattr(self.lib, f"mir_optimize_least_squares_batched_dev_{sfx}")
+        rc = fn(C.byref(settings), C.byref(desc), batch, m, n, _vp(x), _vp(l), _vp(u), bound_stride,
+                _vp(results), _vp(stats), C.c_void_p(stream))
+        self._check(rc)
+        return results
+
+    @staticmethod
+    def results_from_bytes(buf, dtype) -> np.ndarray:
+        """uint8 torch tensor (device or host) -> structured numpy array of Result PODs."""
+        return np.frombuffer(buf.cpu().numpy().tobytes(), dtype=RESULT_DTYPES[np.dtype(dtype)])
