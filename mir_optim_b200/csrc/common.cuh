@@ -49,10 +49,8 @@ __device__ __forceinline__ float  add_rn(float a, float b)   { return __fadd_rn(
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
 
-__device__ __forceinline__ double t_sqrt(double a) { return sqrt(a); }
-__device__ __forceinline__ float  t_sqrt(float a)  { return sqrtf(a); }
-__device__ __forceinline__ double t_exp(double a)  { return exp(a); }
-__device__ __forceinline__ float  t_exp(float a)   { return expf(a); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ float  sub_rn(float a, float b)   { return __fadd_rn(a, -b); }
 __device__ __forceinline__ double t_abs(double a)  { return fabs(a); }
 __device__ __forceinline__ float  t_abs(float a)   { return fabsf(a); }
 __device__ __forceinline__ double t_min(double a, double b) { return fmin(a, b); }   // IEEE minNum, as D's fmin

@@ -21,9 +21,10 @@ static int batched_dev(const typename Num<T>::Settings* settings, const mir_mode
     int rc = require_device(-1);
     if (rc) return rc;
 
-    unsigned long long* counter = nullptr;
-    MIRB200_CUDA(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), stream));
-    MIRB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    if (batch >= 0xffffffffull) { set_error("mir_optim_b200: at most 2^32 - 2 problems per launch"); return MIR_B200_EINVAL; }
+    unsigned int* counter = nullptr;
+    MIRB200_CUDA(cudaMallocAsync((void**)&counter, sizeof(unsigned int), stream));
+    MIRB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
 
     SmallBatchArgs a;
     a.t = model->t; a.y = model->y; a.x = x; a.l = l; a.u = u; a.results = results;

@@ -12,8 +12,8 @@
 // "serial" part (BoxQP / Cholesky / lambda control) needs no communication and no divergence.
 //
 // Equivalences used (all bit-exact with respect to this file's own arithmetic):
-//   * J^T J is rebuilt only when J changed (the reference re-runs syrk every pass, LS:1065; with
-//     unchanged J it returns the same matrix).
+//   * J^T J is rebuilt only when J changed, together with J^T r (the reference re-runs syrk every
+//     pass, LS:1065; with unchanged J it returns the same matrix).
 //   * If the trial point equals x bit for bit, f(trial) == y and trial residual == residual, so
 //     the pass is a rejection (LS:1124-1130); the model evaluation is skipped, fCalls still counts it.
 #pragma once
@@ -29,7 +29,7 @@ struct SmallBatchArgs {
     const void* l;          // T[n] or T[batch*bound_stride]
     const void* u;
     void*       results;    // Result[batch]
-    unsigned long long* counter;   // work queue head (zeroed by the launcher)
+    unsigned int* counter;         // work queue head (zeroed by the launcher); batch < 2^32 per launch
     mir_batch_stats* stats; // may be null
     unsigned long long batch;
     unsigned m;
@@ -37,8 +37,12 @@ struct SmallBatchArgs {
     unsigned flags;         // MIR_MODEL_* flags
 };
 
-template <class Model, class T, int LANES, int R>
-__global__ void __launch_bounds__(128)
+#ifndef MIRB200_MINBLOCKS
+#define MIRB200_MINBLOCKS 1
+#endif
+
+template <class Model, class T, int LANES, int R, bool FD>
+__global__ void __launch_bounds__(128, MIRB200_MINBLOCKS)
 lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
 {
     constexpr int N = Model::N;
@@ -47,8 +51,12 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
 
     const unsigned gmask = group_mask<LANES>();
     const int glane = threadIdx.x & (LANES - 1);
+    // Cross-lane reduction scratch of this group: K = NP + N running sums, one padded row per value.
+    constexpr int K = NP + N;
+    __shared__ T s_red[128 / LANES][K * (LANES + 1) + K];
+    T* const red = s_red[threadIdx.x / LANES];
     const int m = (int)args.m;
-    const bool useFD = (args.flags & MIR_MODEL_FD_JACOBIAN) != 0;
+    constexpr bool useFD = FD;        // g == null semantics (finite differences), compile-time to keep the code small
     const bool gridPerProblem = (args.flags & MIR_MODEL_GRID_PER_PROBLEM) != 0;
     const T* __restrict__ tptr = static_cast<const T*>(args.t);
     const T* __restrict__ yptr = static_cast<const T*>(args.y);
@@ -64,10 +72,11 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
     }
 
     for (;;) {
-        unsigned long long prob = 0;
-        if (glane == 0) prob = atomicAdd(args.counter, 1ull);
-        prob = __shfl_sync(gmask, prob, 0, LANES);
-        if (prob >= args.batch) break;
+        unsigned int prob32 = 0;
+        if (glane == 0) prob32 = atomicAdd(args.counter, 1u);
+        prob32 = __shfl_sync(gmask, prob32, 0, LANES);
+        if (prob32 >= args.batch) break;
+        const unsigned long long prob = prob32;
         ++sProblems;
 
         // ---- load the problem ----
@@ -152,7 +161,6 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
             ret.fCalls = 1;
             bool fConverged = ret.residual <= st.maxGoodResidual;                            // LS:956
             bool needJacobian = true;                                                        // LS:959-971
-            bool jjDirty = true;
             unsigned age = maxAge;
             T lambda = (T)0, mu = (T)1, deltaX_dot = (T)0;
             int status = mir_ls_maxIterations;
@@ -171,10 +179,9 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                 }
                 if (needJacobian) {                                                          // LS:996
                     needJacobian = false;
-                    jjDirty = true;
                     if (age < maxAge) {                                                      // Broyden, LS:999-1007
                         ++age; ++sBroyden;
-                        const T d = (T)1 / deltaX_dot;
+                        const T d = rcp_ni(deltaX_dot);
 #pragma unroll
                         for (int k = 0; k < R; ++k) {
                             T v = mb[k] - yv[k];                                             // axpy(-1, y, mBuffer)
@@ -188,7 +195,7 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         }
                     } else {
                         age = 0; ++sFresh;                                                   // LS:1010
-                        if (!useFD) {                                                        // LS:1011-1015
+                        if constexpr (!useFD) {                                              // LS:1011-1015
                             const typename Model::Pre pre = Model::prepare(x);
 #pragma unroll
                             for (int k = 0; k < R; ++k) {
@@ -197,45 +204,75 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                             }
                             ret.gCalls += 1;
                         } else {                                                             // LS:1018-1049
+#pragma unroll 1
+                            for (int j = 0; j < N; ++j) {          // rolled: parameter j is selected by predication
+                                T save = (T)0, lj = (T)0, uj = (T)0;
 #pragma unroll
-                            for (int j = 0; j < N; ++j) {
-                                T p[N];
-#pragma unroll
-                                for (int i = 0; i < N; ++i) p[i] = x[i];
-                                const T save = x[j];
+                                for (int i = 0; i < N; ++i) if (i == j) { save = x[i]; lj = lo[i]; uj = up[i]; }
                                 T xmh = save - st.jacobianEpsilon;
                                 T xph = save + st.jacobianEpsilon;
-                                xmh = t_max(xmh, lo[j]);
-                                xph = t_min(xph, up[j]);
+                                xmh = t_max(xmh, lj);
+                                xph = t_min(xph, uj);
                                 const T twh = xph - xmh;
-                                if (twh != (T)0) {
-                                    T fp[R], fm[R];
-                                    p[j] = xph; eval(p, fp);
-                                    p[j] = xmh; eval(p, fm);
-                                    const T rt = (T)1 / twh;
+                                T col[R];
 #pragma unroll
-                                    for (int k = 0; k < R; ++k) J[k][j] = (fp[k] - fm[k]) * rt;
+                                for (int k = 0; k < R; ++k) col[k] = (T)0;
+                                if (twh != (T)0) {
+                                    T p[N], fp[R], fm[R];
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) p[i] = (i == j) ? xph : x[i];
+                                    eval(p, fp);
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) p[i] = (i == j) ? xmh : x[i];
+                                    eval(p, fm);
+                                    const T rt = rcp_ni(twh);
+#pragma unroll
+                                    for (int k = 0; k < R; ++k) col[k] = (fp[k] - fm[k]) * rt;
                                     // (the reference evaluates through mBuffer, LS:1036-1039; nothing reads it
                                     //  before the next trial evaluation overwrites it, so it is not mirrored)
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < R; ++k) J[k][j] = (T)0;
                                 }
+#pragma unroll
+                                for (int k = 0; k < R; ++k)
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) if (i == j) J[k][i] = col[k];
                             }
                             ret.fCalls += N;                                                 // LS:1049 (counts tasks)
                         }
                     }
-                    {   // Jy = J^T y, LS:1052
-                        T part[N];
+                    {   // Jy = J^T y (LS:1052) and JJ = J^T J (syrk, LS:1065) in one cross-lane reduction.
+                        // (The reference rebuilds JJ on every pass; J only changes here, so this is the one
+                        //  place it has to be formed.)  Each lane sums its rows, the partials go through shared
+                        //  memory, lane k adds the LANES partials of value k in a fixed order, and every lane
+                        //  reads back the same K totals -- bit-identical replicas, and a rolled loop instead of
+                        //  5*K unrolled shuffles keeps the kernel inside the instruction cache.
+                        T part[K];
 #pragma unroll
-                        for (int i = 0; i < N; ++i) part[i] = (T)0;
+                        for (int i = 0; i < K; ++i) part[i] = (T)0;
 #pragma unroll
                         for (int k = 0; k < R; ++k)
 #pragma unroll
-                            for (int i = 0; i < N; ++i) part[i] += J[k][i] * yv[k];
-                        group_sum_array<LANES, N>(gmask, part);
+                            for (int i = 0; i < N; ++i) {
+                                part[NP + i] += J[k][i] * yv[k];
 #pragma unroll
-                        for (int i = 0; i < N; ++i) Jy[i] = part[i];
+                                for (int j = 0; j <= i; ++j) part[tri(i, j)] += J[k][i] * J[k][j];
+                            }
+                        __syncwarp(gmask);
+#pragma unroll
+                        for (int i = 0; i < K; ++i) red[i * (LANES + 1) + glane] = part[i];
+                        __syncwarp(gmask);
+#pragma unroll 1
+                        for (int v = glane; v < K; v += LANES) {
+                            const T* row = red + v * (LANES + 1);
+                            T s0 = (T)0, s1 = (T)0, s2 = (T)0, s3 = (T)0;
+#pragma unroll 2
+                            for (int i = 0; i < LANES; i += 4) { s0 += row[i]; s1 += row[i + 1]; s2 += row[i + 2]; s3 += row[i + 3]; }
+                            red[K * (LANES + 1) + v] = (s0 + s1) + (s2 + s3);
+                        }
+                        __syncwarp(gmask);
+#pragma unroll
+                        for (int i = 0; i < NP; ++i) JJ[i] = red[K * (LANES + 1) + i];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) Jy[i] = red[K * (LANES + 1) + NP + i];
                     }
                     T gmax = (T)0; bool gnan = false;                                        // LS:1053
 #pragma unroll
@@ -249,22 +286,6 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         age = maxAge;
                         continue;
                     }
-                }
-
-                if (jjDirty) {                                                               // syrk, LS:1065
-                    jjDirty = false;
-                    T part[NP];
-#pragma unroll
-                    for (int i = 0; i < NP; ++i) part[i] = (T)0;
-#pragma unroll
-                    for (int k = 0; k < R; ++k)
-#pragma unroll
-                        for (int i = 0; i < N; ++i)
-#pragma unroll
-                            for (int j = 0; j <= i; ++j) part[tri(i, j)] += J[k][i] * J[k][j];
-                    group_sum_array<LANES, NP>(gmask, part);
-#pragma unroll
-                    for (int i = 0; i < NP; ++i) JJ[i] = part[i];
                 }
 
                 if (!(lambda >= st.minLambda)) {                                             // LS:1067-1072
@@ -292,7 +313,7 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
 #pragma unroll
                 for (int i = 0; i < N; ++i) { dX[i] = add_rn(add_rn(dX[i], x[i]), -x[i]); nd += dX[i] * dX[i]; }
 
-                if (!(t_sqrt(nd) < st.maxStep)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; continue; }   // LS:1101-1106
+                if (!(sqrt_ni(nd) < st.maxStep)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; continue; }   // LS:1101-1106
 
                 T xt[N];                                                                     // LS:1108-1110
                 bool same = true;
@@ -331,7 +352,7 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                 pred = -pred;
                 if (!(pred > (T)0)) { status = mir_ls_furtherImprovement; break; }           // LS:1144-1148
 
-                const T rho = pred / improvement;                                            // LS:1150
+                const T rho = div_ni(pred, improvement);                                            // LS:1150
                 if (rho < st.minStepQuality) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; }   // LS:1152-1156
                 else if (rho >= st.goodStepQuality) lambda = t_max(st.lambdaDecrease * lambda * mu, st.minLambda);   // LS:1158-1161
 
@@ -341,13 +362,13 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                 for (int i = 0; i < N; ++i) xmax = t_max(xmax, t_abs(x[i]));
                 T xn = (T)0;
                 if (xmax > (T)0) {
-                    const T inv = (T)1 / xmax;
+                    const T inv = rcp_ni(xmax);
                     T ss = (T)0;
 #pragma unroll
                     for (int i = 0; i < N; ++i) { const T v = x[i] * inv; ss += v * v; }
-                    xn = xmax * t_sqrt(ss);
+                    xn = xmax * sqrt_ni(ss);
                 }
-                const T sd = t_sqrt(deltaX_dot);
+                const T sd = sqrt_ni(deltaX_dot);
                 if (!(sd > st.absTolerance && xn > sd * st.relTolerance)) {                  // LS:1164-1173
                     if (age == 0) { status = mir_ls_xConverged; break; }
                     age = maxAge;

@@ -1,5 +1,8 @@
 // lm_small_inst.inl -- model dispatch; included by lm_small_inst_d.cu / lm_small_inst_s.cu with REAL defined.
 #include <initializer_list>
+#ifndef MIRB200_GAUSS_LANES
+#define MIRB200_GAUSS_LANES 8
+#endif
 #include "lm_small_launch.cuh"
 
 namespace mirb200 {
@@ -19,7 +22,12 @@ int launch_small_model<REAL>(unsigned model, size_t n, const Num<REAL>::Settings
     case MIR_MODEL_EXPDECAY2:  if (n != 2) return bad_n(2); return launch_small<ModelExpDecay2<T>, T, 32, 1, 4>(st, args, stream);
     case MIR_MODEL_EXPTAU3:    if (n != 3) return bad_n(3); return launch_small<ModelExpTau3<T>, T, 32, 1, 4>(st, args, stream);
     case MIR_MODEL_EXPDECAY3:  if (n != 3) return bad_n(3); return launch_small<ModelExpDecay3<T>, T, 32, 1, 4>(st, args, stream);
-    case MIR_MODEL_GAUSS4:     if (n != 4) return bad_n(4); return launch_small<ModelGauss4<T>, T, 32, 1, 2, 4>(st, args, stream);
+    case MIR_MODEL_GAUSS4:
+        if (n != 4) return bad_n(4);
+        // m <= 64: an 8-lane group per problem (4 problems per warp) measured fastest on B200 (the n-sized
+        // serial part is replicated 8x instead of 32x); larger m: one full warp per problem.
+        if (args.m <= 64) return launch_small<ModelGauss4<T>, T, MIRB200_GAUSS_LANES, 64 / MIRB200_GAUSS_LANES>(st, args, stream);
+        return launch_small<ModelGauss4<T>, T, 32, 4>(st, args, stream);
     case MIR_MODEL_SUMEXP:
         if (n == 4) return launch_small<ModelSumExp<T, 4>, T, 32, 2, 4>(st, args, stream);
         if (n == 8) return launch_small<ModelSumExp<T, 8>, T, 32, 2, 4>(st, args, stream);

@@ -6,10 +6,10 @@
 
 namespace mirb200 {
 
-template <class Model, class T, int LANES, int R>
-int launch_small_one(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+template <class Model, class T, int LANES, int R, bool FD>
+int launch_small_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
-    auto kern = lm_small_kernel<Model, T, LANES, R>;
+    auto kern = lm_small_kernel<Model, T, LANES, R, FD>;
     int blocksPerSM = 0;
     MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, 128, 0));
     if (blocksPerSM < 1) blocksPerSM = 1;
@@ -20,6 +20,13 @@ int launch_small_one(const typename Num<T>::Settings& st, const SmallBatchArgs& 
     kern<<<(unsigned)grid, 128, 0, stream>>>(st, args);
     count_launch();
     return check_cuda(cudaGetLastError(), "lm_small_kernel launch");
+}
+
+template <class Model, class T, int LANES, int R>
+int launch_small_one(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    return (args.flags & MIR_MODEL_FD_JACOBIAN) ? launch_small_fd<Model, T, LANES, R, true>(st, args, stream)
+                                                : launch_small_fd<Model, T, LANES, R, false>(st, args, stream);
 }
 
 // Rs...: the rows-per-lane instantiations compiled for this model, ascending.

@@ -7,8 +7,15 @@
 // the GPU counterparts of the reference's LeastSquaresFunction / LeastSquaresJacobian
 // callbacks (least_squares.d:73-80); the first five are the reference's own unit-test
 // problems (least_squares.d:217-434).
+//
+// Every operation is an explicitly rounded IEEE operation (mul_rn/add_rn/sub_rn, correctly
+// rounded division and sqrt, exp_repro): no FMA contraction, no fast-math.  A host callback
+// that performs the same operations in the same order (oracle/models_oracle.cpp, compiled with
+// -ffp-contract=off) therefore returns bit-identical residuals and Jacobian rows, which is what
+// lets finite-difference runs be compared with the CPU reference at 1e-10 (see repro_math.cuh).
 #pragma once
 #include "common.cuh"
+#include "repro_math.cuh"
 
 namespace mirb200 {
 
@@ -19,7 +26,7 @@ template <class T> struct ModelLinear2 {
     static constexpr int N = 2; static constexpr bool kHasData = false;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int row, T, T) { return row == 0 ? p[0] : (T)2 - p[1]; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int row, T, T) { return row == 0 ? p[0] : sub_rn((T)2, p[1]); }
     __device__ static void jacobian(const Pre&, const T (&)[N], int row, T, T (&J)[N]) {
         J[0] = row == 0 ? (T)1 : (T)0; J[1] = row == 0 ? (T)0 : (T)-1;
     }
@@ -31,10 +38,10 @@ template <class T> struct ModelRosenbrock {
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int row, T, T) {
-        return row == 0 ? (T)10 * (p[1] - p[0] * p[0]) : (T)1 - p[0];
+        return row == 0 ? mul_rn((T)10, sub_rn(p[1], mul_rn(p[0], p[0]))) : sub_rn((T)1, p[0]);
     }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int row, T, T (&J)[N]) {
-        J[0] = row == 0 ? (T)-20 * p[0] : (T)-1; J[1] = row == 0 ? (T)10 : (T)0;
+        J[0] = row == 0 ? mul_rn((T)-20, p[0]) : (T)-1; J[1] = row == 0 ? (T)10 : (T)0;
     }
 };
 
@@ -43,10 +50,12 @@ template <class T> struct ModelSqrtCircle {
     static constexpr int N = 2; static constexpr bool kHasData = false;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T, T) { return t_sqrt((T)1 - (p[0] * p[0] + p[1] * p[1])); }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T, T) {
+        return sqrt_ni(sub_rn((T)1, add_rn(mul_rn(p[0], p[0]), mul_rn(p[1], p[1]))));
+    }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T, T (&J)[N]) {
-        T s = t_sqrt((T)1 - (p[0] * p[0] + p[1] * p[1]));
-        J[0] = -p[0] / s; J[1] = -p[1] / s;
+        const T s = sqrt_ni(sub_rn((T)1, add_rn(mul_rn(p[0], p[0]), mul_rn(p[1], p[1]))));
+        J[0] = div_ni(-p[0], s); J[1] = div_ni(-p[1], s);
     }
 };
 
@@ -55,9 +64,12 @@ template <class T> struct ModelExpDecay2 {
     static constexpr int N = 2; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) { return p[0] * t_exp(-t * p[1]) - y; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
+        return sub_rn(mul_rn(p[0], exp_repro(mul_rn(-t, p[1]))), y);
+    }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        T e = t_exp(-t * p[1]); J[0] = e; J[1] = -(p[0] * t) * e;
+        const T e = exp_repro(mul_rn(-t, p[1]));
+        J[0] = e; J[1] = mul_rn(-mul_rn(p[0], t), e);
     }
 };
 
@@ -66,9 +78,12 @@ template <class T> struct ModelExpTau3 {
     static constexpr int N = 3; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) { return p[0] * t_exp(-t / p[1]) + p[2] - y; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
+        return sub_rn(add_rn(mul_rn(p[0], exp_repro(div_ni(-t, p[1]))), p[2]), y);
+    }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        T e = t_exp(-t / p[1]); J[0] = e; J[1] = p[0] * e * t / (p[1] * p[1]); J[2] = (T)1;
+        const T e = exp_repro(div_ni(-t, p[1]));
+        J[0] = e; J[1] = div_ni(mul_rn(mul_rn(p[0], e), t), mul_rn(p[1], p[1])); J[2] = (T)1;
     }
 };
 
@@ -77,9 +92,12 @@ template <class T> struct ModelExpDecay3 {
     static constexpr int N = 3; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) { return p[0] * t_exp(-p[1] * t) + p[2] - y; }
+    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
+        return sub_rn(add_rn(mul_rn(p[0], exp_repro(mul_rn(-p[1], t))), p[2]), y);
+    }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        T e = t_exp(-p[1] * t); J[0] = e; J[1] = -(p[0] * t) * e; J[2] = (T)1;
+        const T e = exp_repro(mul_rn(-p[1], t));
+        J[0] = e; J[1] = mul_rn(-mul_rn(p[0], t), e); J[2] = (T)1;
     }
 };
 
@@ -88,16 +106,17 @@ template <class T> struct ModelExpDecay3 {
 template <class T> struct ModelGauss4 {
     static constexpr int N = 4; static constexpr bool kHasData = true;
     struct Pre { T is; };
-    __device__ static Pre prepare(const T (&p)[N]) { return {(T)1 / p[2]}; }
+    __device__ static Pre prepare(const T (&p)[N]) { return {rcp_ni(p[2])}; }
     __device__ static T residual(const Pre& q, const T (&p)[N], int, T t, T y) {
-        T z = (t - p[1]) * q.is;
-        return p[0] * t_exp((T)-0.5 * (z * z)) + p[3] - y;
+        const T z = mul_rn(sub_rn(t, p[1]), q.is);
+        return sub_rn(add_rn(mul_rn(p[0], exp_repro(mul_rn((T)-0.5, mul_rn(z, z)))), p[3]), y);
     }
     __device__ static void jacobian(const Pre& q, const T (&p)[N], int, T t, T (&J)[N]) {
-        T z = (t - p[1]) * q.is;
-        T e = t_exp((T)-0.5 * (z * z));
-        T ae = p[0] * e;
-        J[0] = e; J[1] = ae * z * q.is; J[2] = ae * (z * z) * q.is; J[3] = (T)1;
+        const T z = mul_rn(sub_rn(t, p[1]), q.is);
+        const T zz = mul_rn(z, z);
+        const T e = exp_repro(mul_rn((T)-0.5, zz));
+        const T ae = mul_rn(p[0], e);
+        J[0] = e; J[1] = mul_rn(mul_rn(ae, z), q.is); J[2] = mul_rn(mul_rn(ae, zz), q.is); J[3] = (T)1;
     }
 };
 
@@ -108,16 +127,16 @@ template <class T, int N_> struct ModelSumExp {
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
-        T acc = 0;
+        T acc = (T)0;
 #pragma unroll
-        for (int k = 0; k < N; k += 2) acc += p[k] * t_exp(-p[k + 1] * t);
-        return acc - y;
+        for (int k = 0; k < N; k += 2) acc = add_rn(acc, mul_rn(p[k], exp_repro(mul_rn(-p[k + 1], t))));
+        return sub_rn(acc, y);
     }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
 #pragma unroll
         for (int k = 0; k < N; k += 2) {
-            T e = t_exp(-p[k + 1] * t);
-            J[k] = e; J[k + 1] = -(p[k] * t) * e;
+            const T e = exp_repro(mul_rn(-p[k + 1], t));
+            J[k] = e; J[k + 1] = mul_rn(-mul_rn(p[k], t), e);
         }
     }
 };

@@ -5,10 +5,13 @@
  * LeastSquaresJacobianBetterC signatures, LS:78-80) for the built-in models named by
  * mir_model_id, plus an OpenMP driver that runs the oracle LM (lm_oracle.cpp ==
  * LS:877-1176) over a batch of independent problems.  The formulas are written here
- * independently of the CUDA functors (mir_optim_b200/csrc/models.cuh) with plain libm calls;
- * the first five are the reference's own unit-test problems (LS:217-434).
+ * independently of the CUDA functors (mir_optim_b200/csrc/models.cuh); the first five are the
+ * reference's own unit-test problems (LS:217-434).  exp is oracle_math::exp_repro (repro_math.h)
+ * and the file is compiled with -ffp-contract=off, so every operation rounds exactly like the
+ * device functor's explicitly rounded operation sequence: CPU and GPU see identical residuals.
  */
 #include "../include/mir_optim_b200.h"
+#include "repro_math.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -31,6 +34,8 @@ typedef struct oracle_model_ctx {
 
 namespace {
 
+using oracle_math::exp_repro;
+
 template <class T>
 void model_f(void* vctx, size_t m, size_t n, const T* p, T* r)
 {
@@ -42,25 +47,25 @@ void model_f(void* vctx, size_t m, size_t n, const T* p, T* r)
     case MIR_MODEL_ROSENBROCK: r[0] = 10 * (p[1] - p[0] * p[0]); r[1] = 1 - p[0]; break;   // LS:261-265
     case MIR_MODEL_SQRTCIRCLE: r[0] = std::sqrt(1 - (p[0] * p[0] + p[1] * p[1])); break;   // LS:427-430
     case MIR_MODEL_EXPDECAY2:                                                               // LS:347, 360
-        for (size_t i = 0; i < m; ++i) r[i] = p[0] * std::exp(-t[i] * p[1]) - y[i];
+        for (size_t i = 0; i < m; ++i) r[i] = p[0] * exp_repro(-t[i] * p[1]) - y[i];
         break;
     case MIR_MODEL_EXPTAU3:                                                                 // LS:378, 390
-        for (size_t i = 0; i < m; ++i) r[i] = p[0] * std::exp(-t[i] / p[1]) + p[2] - y[i];
+        for (size_t i = 0; i < m; ++i) r[i] = p[0] * exp_repro(-t[i] / p[1]) + p[2] - y[i];
         break;
     case MIR_MODEL_EXPDECAY3:
-        for (size_t i = 0; i < m; ++i) r[i] = p[0] * std::exp(-p[1] * t[i]) + p[2] - y[i];
+        for (size_t i = 0; i < m; ++i) r[i] = p[0] * exp_repro(-p[1] * t[i]) + p[2] - y[i];
         break;
     case MIR_MODEL_GAUSS4: {
         const T is = 1 / p[2];
         for (size_t i = 0; i < m; ++i) {
             T z = (t[i] - p[1]) * is;
-            r[i] = p[0] * std::exp((T)-0.5 * (z * z)) + p[3] - y[i];
+            r[i] = p[0] * exp_repro((T)-0.5 * (z * z)) + p[3] - y[i];
         }
         break; }
     case MIR_MODEL_SUMEXP:
         for (size_t i = 0; i < m; ++i) {
             T acc = 0;
-            for (size_t k = 0; k + 1 < n; k += 2) acc += p[k] * std::exp(-p[k + 1] * t[i]);
+            for (size_t k = 0; k + 1 < n; k += 2) acc += p[k] * exp_repro(-p[k + 1] * t[i]);
             r[i] = acc - y[i];
         }
         break;
@@ -69,7 +74,7 @@ void model_f(void* vctx, size_t m, size_t n, const T* p, T* r)
             T acc = p[n - 2] + p[n - 1] * t[i];
             for (size_t k = 0; k + 3 <= n - 2; k += 3) {
                 T z = (t[i] - p[k + 1]) * (1 / p[k + 2]);
-                acc += p[k] * std::exp((T)-0.5 * (z * z));
+                acc += p[k] * exp_repro((T)-0.5 * (z * z));
             }
             r[i] = acc - y[i];
         }
@@ -91,19 +96,19 @@ void model_g(void* vctx, size_t m, size_t n, const T* p, T* J)
         J[0] = -p[0] / s; J[1] = -p[1] / s; break; }
     case MIR_MODEL_EXPDECAY2:
         for (size_t i = 0; i < m; ++i) {
-            T e = std::exp(-t[i] * p[1]);
+            T e = exp_repro(-t[i] * p[1]);
             J[i * n + 0] = e; J[i * n + 1] = -(p[0] * t[i]) * e;
         }
         break;
     case MIR_MODEL_EXPTAU3:
         for (size_t i = 0; i < m; ++i) {
-            T e = std::exp(-t[i] / p[1]);
-            J[i * n + 0] = e; J[i * n + 1] = p[0] * e * t[i] / (p[1] * p[1]); J[i * n + 2] = 1;
+            T e = exp_repro(-t[i] / p[1]);
+            J[i * n + 0] = e; J[i * n + 1] = ((p[0] * e) * t[i]) / (p[1] * p[1]); J[i * n + 2] = 1;
         }
         break;
     case MIR_MODEL_EXPDECAY3:
         for (size_t i = 0; i < m; ++i) {
-            T e = std::exp(-p[1] * t[i]);
+            T e = exp_repro(-p[1] * t[i]);
             J[i * n + 0] = e; J[i * n + 1] = -(p[0] * t[i]) * e; J[i * n + 2] = 1;
         }
         break;
@@ -111,18 +116,18 @@ void model_g(void* vctx, size_t m, size_t n, const T* p, T* J)
         const T is = 1 / p[2];
         for (size_t i = 0; i < m; ++i) {
             T z = (t[i] - p[1]) * is;
-            T e = std::exp((T)-0.5 * (z * z));
+            T e = exp_repro((T)-0.5 * (z * z));
             T ae = p[0] * e;
             J[i * n + 0] = e;
-            J[i * n + 1] = ae * z * is;
-            J[i * n + 2] = ae * (z * z) * is;
+            J[i * n + 1] = (ae * z) * is;
+            J[i * n + 2] = (ae * (z * z)) * is;
             J[i * n + 3] = 1;
         }
         break; }
     case MIR_MODEL_SUMEXP:
         for (size_t i = 0; i < m; ++i)
             for (size_t k = 0; k + 1 < n; k += 2) {
-                T e = std::exp(-p[k + 1] * t[i]);
+                T e = exp_repro(-p[k + 1] * t[i]);
                 J[i * n + k] = e; J[i * n + k + 1] = -(p[k] * t[i]) * e;
             }
         break;
@@ -131,9 +136,9 @@ void model_g(void* vctx, size_t m, size_t n, const T* p, T* J)
             for (size_t k = 0; k + 3 <= n - 2; k += 3) {
                 T is = 1 / p[k + 2];
                 T z = (t[i] - p[k + 1]) * is;
-                T e = std::exp((T)-0.5 * (z * z));
+                T e = exp_repro((T)-0.5 * (z * z));
                 T ae = p[k] * e;
-                J[i * n + k] = e; J[i * n + k + 1] = ae * z * is; J[i * n + k + 2] = ae * (z * z) * is;
+                J[i * n + k] = e; J[i * n + k + 1] = (ae * z) * is; J[i * n + k + 2] = (ae * (z * z)) * is;
             }
             J[i * n + n - 2] = 1; J[i * n + n - 1] = t[i];
         }
