@@ -12,6 +12,7 @@
 //                 Active-set sub-systems are compacted through the ascending free-index list,
 //                 exactly like boxcqp.d:269-305.
 #pragma once
+#include <type_traits>
 #include "boxqp_small.cuh"   // KBN
 #include "common.cuh"
 
@@ -98,11 +99,11 @@ __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
     const T amax = cta_reduce_max<T, NT>(mx, w.red);
     bool equil = false;
     if (smin > (T)0) {
-        const T scond = t_sqrt(smin) / t_sqrt(amax);
+        const T scond = sqrt_ni(smin) / sqrt_ni(amax);
         equil = !(scond >= (T)0.1 && amax >= Num<T>::small_() && amax <= Num<T>::large_());
     }
     for (int a = tid; a < s; a += NT) {
-        const T sa = equil ? (T)1 / t_sqrt(A(a, a)) : (T)1;
+        const T sa = equil ? (T)1 / sqrt_ni(A(a, a)) : (T)1;
         w.sc[a] = sa;
         b[a] = equil ? sa * b[a] : b[a];
     }
@@ -118,7 +119,7 @@ __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
     const int tx = tid % TK, ty = tid / TK;
     for (int j = 0; j < s; ++j) {
         const T d = F[j * ldf + j];
-        if (!(d > (T)0)) return j + 1;                      // uniform: every thread reads the same d
+        if (d <= (T)0) return j + 1;     // uniform (every thread reads the same d).  A NaN pivot passes, as in OpenBLAS' potrf
         const T inv = (T)1 / d;
         for (int i = j + 1 + ty; i < s; i += TI) {
             const T li = F[i * ldf + j] * inv;

@@ -82,7 +82,7 @@ __device__ __forceinline__ int posvx_small(const T (&JJ)[N * (N + 1) / 2], T lam
         T ajj = a[tri(j, j)];
 #pragma unroll
         for (int k = 0; k < j; ++k) ajj -= f[tri(j, k)] * f[tri(j, k)];
-        if (!(ajj > (T)0)) return j + 1;                           // ajj <= 0 or NaN
+        if (ajj <= (T)0) return j + 1;          // breakdown; a NaN pivot passes through, as in OpenBLAS' potrf (potf2: `ajj <= 0`)
         ajj = sqrt_ni(ajj);
         f[tri(j, j)] = ajj;
         const T r = rcp_ni(ajj);

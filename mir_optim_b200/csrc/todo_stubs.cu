@@ -14,12 +14,6 @@ void mir_b200_device_model_d(void*, size_t, size_t, const double*, double*) {}
 void mir_b200_device_model_jac_d(void*, size_t, size_t, const double*, double*) {}
 void mir_b200_device_model_s(void*, size_t, size_t, const float*, float*) {}
 void mir_b200_device_model_jac_s(void*, size_t, size_t, const float*, float*) {}
-int mir_solve_box_qp_d(const mir_box_qp_settings_d*, size_t, const double*, const double*, const double*, const double*, double*) { return -nyi("mir_solve_box_qp_d"); }
-int mir_solve_box_qp_s(const mir_box_qp_settings_s*, size_t, const float*, const float*, const float*, const float*, float*) { return -nyi("mir_solve_box_qp_s"); }
-int mir_solve_box_qp_batched_d(const mir_box_qp_settings_d*, size_t, size_t, const double*, const double*, const double*, const double*, double*, int32_t*, uint32_t*, int) { return nyi("mir_solve_box_qp_batched_d"); }
-int mir_solve_box_qp_batched_s(const mir_box_qp_settings_s*, size_t, size_t, const float*, const float*, const float*, const float*, float*, int32_t*, uint32_t*, int) { return nyi("mir_solve_box_qp_batched_s"); }
-int mir_solve_box_qp_batched_dev_d(const mir_box_qp_settings_d*, size_t, size_t, const double*, const double*, const double*, const double*, double*, int32_t*, uint32_t*, void*) { return nyi("mir_solve_box_qp_batched_dev_d"); }
-int mir_solve_box_qp_batched_dev_s(const mir_box_qp_settings_s*, size_t, size_t, const float*, const float*, const float*, const float*, float*, int32_t*, uint32_t*, void*) { return nyi("mir_solve_box_qp_batched_dev_s"); }
 int mir_optimize_least_squares_sharded_d(const mir_least_squares_settings_d*, const mir_model_desc*, size_t, size_t, double*, const double*, const double*, void*, void*, mir_least_squares_result_d*, mir_batch_stats*) { return nyi("mir_optimize_least_squares_sharded_d"); }
 int mir_b200_nccl_unique_id(void*) { return nyi("nccl"); }
 int mir_b200_nccl_comm_init(void**, int, const void*, int) { return nyi("nccl"); }

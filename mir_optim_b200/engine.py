@@ -110,6 +110,44 @@ class Engine(ReferenceAPI):
         self._check(rc)
         return results
 
+    # -- solveBoxQP (boxcqp.d:85-102) -----------------------------------------------------
+    def solve_box_qp(self, P: np.ndarray, q: np.ndarray, l: np.ndarray, u: np.ndarray, x: np.ndarray, settings=None):
+        """argmin 1/2 x'Px + q'x, l <= x <= u.  Only the lower triangle of P (row-major) is read.  Returns BoxQPStatus."""
+        sfx = _types(P.dtype)[0]
+        n = q.shape[0]
+        assert P.shape == (n, n) and P.flags.c_contiguous
+        st = getattr(self.lib, f"mir_solve_box_qp_{sfx}")(C.byref(settings) if settings is not None else None, n,
+                                                          _vp(P), _vp(q), _vp(l), _vp(u), _vp(x))
+        if st < 0:
+            self._check(-st)
+        return _abi.BoxQPStatus(st)
+
+    def solve_box_qp_batched(self, P: np.ndarray, q: np.ndarray, l: np.ndarray, u: np.ndarray, settings=None, device: int = -1):
+        """P (batch, n, n), q/l/u (batch, n) host arrays.  Returns (x, status int32[batch], iterations uint32[batch])."""
+        sfx = _types(P.dtype)[0]
+        batch, n = q.shape
+        assert P.shape == (batch, n, n) and P.flags.c_contiguous and q.flags.c_contiguous
+        l = np.ascontiguousarray(l, dtype=P.dtype); u = np.ascontiguousarray(u, dtype=P.dtype)
+        x = np.zeros((batch, n), dtype=P.dtype)
+        status = np.full(batch, -1, dtype=np.int32); iters = np.zeros(batch, dtype=np.uint32)
+        rc = getattr(self.lib, f"mir_solve_box_qp_batched_{sfx}")(C.byref(settings) if settings is not None else None, batch, n,
+                                                                  _vp(P), _vp(q), _vp(l), _vp(u), _vp(x), _vp(status), _vp(iters), device)
+        self._check(rc)
+        return x, status, iters
+
+    def solve_box_qp_batched_device(self, P, q, l, u, x, status, iterations=None, settings=None, stream=None):
+        """torch CUDA tensors; asynchronous on torch's current stream."""
+        import torch
+        dt = np.dtype({torch.float64: np.float64, torch.float32: np.float32}[P.dtype])
+        sfx = _types(dt)[0]
+        batch, n = q.shape
+        if stream is None:
+            stream = torch.cuda.current_stream(P.device).cuda_stream
+        rc = getattr(self.lib, f"mir_solve_box_qp_batched_dev_{sfx}")(C.byref(settings) if settings is not None else None, batch, n,
+                                                                      _vp(P), _vp(q), _vp(l), _vp(u), _vp(x), _vp(status),
+                                                                      _vp(iterations), C.c_void_p(stream))
+        self._check(rc)
+
     @staticmethod
     def results_from_bytes(buf, dtype) -> np.ndarray:
         """uint8 torch tensor (device or host) -> structured numpy array of Result PODs."""

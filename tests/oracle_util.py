@@ -98,15 +98,18 @@ def oracle_batched_mp(lib, settings, model, x0, l, u, t=None, y=None, m=None, fd
     return x, res, procs
 
 
-def self_sensitivity(lib, settings, wl, dtype=np.float64, fd=None, sample=17):
-    """The reference algorithm's own conditioning: run the oracle on the workload and on a copy whose sample
-    `sample` of every problem is moved by ONE ulp.  Returns (x, results, dx_rel, dres_rel) of the unperturbed run
-    and the per-problem relative deviations between the two runs.  (a 1-ulp change moves
-    final parameters by ~sigma * 1e-7 and flips 10-30 % of the termination statuses.)"""
+def self_sensitivity(lib, settings, wl, dtype=np.float64, fd=None, seed=99):
+    """The reference algorithm's own conditioning: run the oracle on the workload and on a copy whose samples are
+    each moved by ONE ulp (up or down at random) -- rounding-level input noise, which is what a different
+    summation order or exp implementation amounts to.  Returns (x, results, dx_rel, dres_rel) of the unperturbed
+    run and the per-problem relative deviations between the two runs.  (a 1-ulp change
+    moves final parameters by ~sigma * 1e-7 and flips 10-30 % of the termination statuses.)"""
     fd = wl.fd_jacobian if fd is None else fd
     a = dict(t=wl.t.astype(dtype), fd_jacobian=fd)
-    x1, r1, _ = oracle_batched_mp(lib, settings, wl.model, wl.x0.astype(dtype), wl.l.astype(dtype), wl.u.astype(dtype), y=wl.y.astype(dtype), **a)
-    y2 = wl.y.astype(dtype).copy(); y2[:, sample] = np.nextafter(y2[:, sample], np.inf)
+    y = wl.y.astype(dtype)
+    x1, r1, _ = oracle_batched_mp(lib, settings, wl.model, wl.x0.astype(dtype), wl.l.astype(dtype), wl.u.astype(dtype), y=y, **a)
+    up = np.random.default_rng(seed).random(y.shape) < 0.5
+    y2 = np.where(up, np.nextafter(y, dtype(np.inf)), np.nextafter(y, dtype(-np.inf))).astype(dtype)
     x2, r2, _ = oracle_batched_mp(lib, settings, wl.model, wl.x0.astype(dtype), wl.l.astype(dtype), wl.u.astype(dtype), y=y2, **a)
     return x1, r1, rel_err(x1, x2), rel_err(r1["residual"], r2["residual"])
 
