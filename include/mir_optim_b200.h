@@ -347,6 +347,11 @@ int mir_optimize_least_squares_sharded_d(
     void* nccl_comm, void* cuda_stream,
     mir_least_squares_result_d* result, mir_batch_stats* stats);
 
+/* J^T J alone (the FP64-tensor SYRK of the large-problem path; replaces syrk at LS:1065): J is rows x ldj
+ * row-major on the device (rows % 32 == 0, ldj even, n <= ldj <= 128); packed receives the lower triangle
+ * by rows, n(n+1)/2 doubles (device).  Asynchronous on cuda_stream.  For roofline measurements and tests. */
+int mir_b200_syrk_lower_dev_d(const double* J, size_t rows, size_t n, size_t ldj, double* packed, void* cuda_stream);
+
 /* NCCL bootstrap helpers so that a host runtime without NCCL bindings (ctypes, D) can build the
  * communicator: rank 0 calls get_unique_id (128 bytes), shares it by any means, all call init. */
 int  mir_b200_nccl_unique_id(void* id128);

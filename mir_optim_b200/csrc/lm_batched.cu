@@ -95,6 +95,17 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     return rc;
 }
 
+// used by the legacy single-problem entry (lm_large.cu) for shapes the register-resident kernel covers
+template <class T>
+int batched_host_entry(const typename Num<T>::Settings* settings, const mir_model_desc* model, size_t batch, size_t m, size_t n,
+                       T* x, const T* l, const T* u, size_t bound_stride, typename Num<T>::Result* results,
+                       mir_batch_stats* stats, int device)
+{ return batched_host<T>(settings, model, batch, m, n, x, l, u, bound_stride, results, stats, device); }
+template int batched_host_entry<double>(const mir_least_squares_settings_d*, const mir_model_desc*, size_t, size_t, size_t, double*, const double*,
+                                        const double*, size_t, mir_least_squares_result_d*, mir_batch_stats*, int);
+template int batched_host_entry<float>(const mir_least_squares_settings_s*, const mir_model_desc*, size_t, size_t, size_t, float*, const float*,
+                                       const float*, size_t, mir_least_squares_result_s*, mir_batch_stats*, int);
+
 }  // namespace mirb200
 
 using namespace mirb200;

@@ -1,0 +1,529 @@
+// lm_large.cuh -- device side of the single-large-problem Levenberg-Marquardt engine
+// (m >> n, n <= 128; BASELINE configs[0] and configs[3]).  Follows
+// optimizeLeastSquaresImplGeneric!T, least_squares.d:877-1176 (line cites inline).
+//
+// One LM pass (one trip round the do-while at LS:972-1175) is a fixed sequence of kernels that all
+// read a device-resident control block (LargeCtl) and turn themselves into no-ops when the pass
+// does not need them, so the host enqueues passes blindly -- there is no per-iteration host
+// round trip; the host only polls `done` every few passes:
+//
+//   jac / fd-jac / broyden   (row-parallel; fresh J or LS:1001-1006 rank-1 update, fused J^T y)
+//   syrk_dmma + reduce       (J^T J on the FP64 tensor pipe, syrk_dmma.cuh)
+//   [all-reduce packed]      (row-sharded runs: n(n+1)/2 + n doubles over NCCL)
+//   ctl_mid                  (1 CTA: g-test, lambda init, BOXCQP step, trial point)
+//   eval                     (row-parallel residuals at the trial point + ||r||^2)
+//   [all-reduce rr]          (1 double)
+//   ctl_post                 (1 CTA: accept/reject, gain ratio, lambda update, convergence,
+//                             loop guards of the NEXT pass LS:974-995 and its Jacobian mode)
+//
+// Every rank of a sharded run executes ctl_mid / ctl_post redundantly on bit-identical inputs
+// (NCCL all-reduce hands every rank the same bits), so all ranks take the same branches.
+//
+// J is materialised (the Broyden update needs it in place, LS:1003-1006): row-major, row pitch
+// ldj = n rounded up to even, rows padded with zeros to a multiple of SYRK_KT.  y and mBuffer are
+// two m-vectors selected by ctl->ysel (the reference swaps the slices, LS:1136).
+#pragma once
+#include "boxqp_cta.cuh"
+#include "models_large.cuh"
+#include "syrk_dmma.cuh"
+
+namespace mirb200 {
+
+constexpr int LARGE_NMAX = 128;
+constexpr int LARGE_NP_MAX = LARGE_NMAX * (LARGE_NMAX + 1) / 2;
+constexpr int LARGE_TILE = 32;       // rows per Jacobian tile
+constexpr int LARGE_CTL_THREADS = 128;
+
+enum { JAC_NONE = 0, JAC_BROYDEN = 1, JAC_FRESH = 2 };
+
+template <class T> struct LargeCtl {
+    typename Num<T>::Settings st;
+    int n, ldj;
+    unsigned maxAge;
+    int hasG;                    // analytic Jacobian supplied (g != null)
+    // loop state, LS:959-971
+    T lambda, mu, residual, deltaX_dot, nd;
+    unsigned age, iterations, fCalls, gCalls;
+    int status, needJacobian, fConverged;
+    // per-pass flags
+    int jacMode, doEval, skipRest, done, ysel, initPhase;
+    unsigned int ticket[4];      // last-block tickets of the row-parallel kernels
+    unsigned long long passes, accepted, fresh, broyden, evals, qpSolves, qpIters;
+    T rr;                        // ||f(trial)||^2 (all-reduced in place)
+    T x[LARGE_NMAX], xt[LARGE_NMAX], l[LARGE_NMAX], u[LARGE_NMAX], dX[LARGE_NMAX], Jy[LARGE_NMAX];
+    T JJ[LARGE_NMAX * LARGE_NMAX];                   // lower triangle, row-major, undamped
+    T packed[LARGE_NP_MAX + LARGE_NMAX];             // [lower(J^T J) by rows | J^T y]  (all-reduced in place)
+};
+
+// ---------------------------------------------------------------------------------------------
+// small deterministic CTA reductions
+// ---------------------------------------------------------------------------------------------
+template <class T, int NT> __device__ __forceinline__ T cta_sum_fixed(T v, T* red)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = red[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) r += red[w];
+    return r;
+}
+
+// LS:974-995 guards + choice of the Jacobian work for the pass that follows (LS:996-1015 bookkeeping).
+template <class T> __device__ void large_begin_pass(LargeCtl<T>* c)
+{
+    // single thread
+    c->jacMode = JAC_NONE; c->doEval = 0; c->skipRest = 0;
+    if (c->done) return;
+    ++c->passes;
+    if (c->fConverged) { c->status = mir_ls_fConverged; c->done = 1; return; }                     // LS:974-978
+    if (!(c->lambda <= c->st.maxLambda)) { c->status = mir_ls_furtherImprovement; c->done = 1; return; }   // LS:979-983
+    if (c->mu > (T)16 && c->age) { c->needJacobian = 1; c->age = c->maxAge; c->mu = (T)1; }        // LS:984-989
+    bool nan = false;                                                                              // LS:990-995
+    for (int i = 0; i < c->n; ++i) nan = nan || !(c->x[i] <= c->x[i]);
+    if (nan) { c->status = mir_ls_numericError; c->done = 1; return; }
+    if (c->needJacobian) {                                                                         // LS:996-998
+        c->needJacobian = 0;
+        if (c->age < c->maxAge) { ++c->age; c->jacMode = JAC_BROYDEN; ++c->broyden; }              // LS:999-1007
+        else {
+            c->age = 0; c->jacMode = JAC_FRESH; ++c->fresh;                                        // LS:1010
+            if (c->hasG) c->gCalls += 1;                                                           // LS:1014
+            else c->fCalls += (unsigned)c->n;                                                      // LS:1049
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual evaluation: out = f(xt) for this rank's rows, rr = sum of squares  (LS:953-955, 1113-1115)
+// ---------------------------------------------------------------------------------------------
+template <class T> struct EvalArgs {
+    LargeCtl<T>* ctl;
+    const T* t; const T* yobs;
+    T* buf0; T* buf1;           // y / mBuffer pair
+    T* partRR;                  // gridDim.x partial sums
+    long long rows;
+};
+
+template <class Model, class T>
+__global__ void __launch_bounds__(256) large_eval_kernel(const EvalArgs<T> a)
+{
+    LargeCtl<T>* c = a.ctl;
+    if (c->done || !c->doEval) return;
+    __shared__ T sp[LARGE_NMAX], saux[LARGE_NMAX], red[8];
+    __shared__ bool last;
+    const int n = c->n, tid = threadIdx.x;
+    for (int k = tid; k < n; k += 256) { const T v = c->xt[k]; sp[k] = v; saux[k] = Model::aux_of(k, n, v); }
+    __syncthreads();
+    T* out = c->ysel ? a.buf0 : a.buf1;        // the trial residuals go to mBuffer = the buffer that is not y
+    ParamView<T> pv{sp, saux, -1, (T)0, (T)0};
+    T acc = (T)0;
+    for (long long row = (long long)blockIdx.x * 256 + tid; row < a.rows; row += (long long)gridDim.x * 256) {
+        const T r = Model::residual(pv, n, a.t[row], a.yobs[row]);
+        out[row] = r;
+        acc += r * r;
+    }
+    const T s = cta_sum_fixed<T, 256>(acc, red);
+    if (tid == 0) {
+        a.partRR[blockIdx.x] = s;
+        __threadfence();
+        last = atomicAdd(&c->ticket[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        T v = (T)0;
+        for (int i = tid; i < (int)gridDim.x; i += 256) v += a.partRR[i];
+        const T tot = cta_sum_fixed<T, 256>(v, red);
+        if (tid == 0) { c->rr = tot; c->ticket[0] = 0; ++c->evals; }
+    }
+}
+
+// rr of a residual vector that is already in the mBuffer (host-callback mode)
+template <class T>
+__global__ void __launch_bounds__(256) large_rr_kernel(const EvalArgs<T> a)
+{
+    LargeCtl<T>* c = a.ctl;
+    if (c->done || !c->doEval) return;
+    __shared__ T red[8];
+    __shared__ bool last;
+    const int tid = threadIdx.x;
+    const T* in = c->ysel ? a.buf0 : a.buf1;
+    T acc = (T)0;
+    for (long long row = (long long)blockIdx.x * 256 + tid; row < a.rows; row += (long long)gridDim.x * 256) { const T r = in[row]; acc += r * r; }
+    const T s = cta_sum_fixed<T, 256>(acc, red);
+    if (tid == 0) { a.partRR[blockIdx.x] = s; __threadfence(); last = atomicAdd(&c->ticket[0], 1u) == gridDim.x - 1; }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        T v = (T)0;
+        for (int i = tid; i < (int)gridDim.x; i += 256) v += a.partRR[i];
+        const T tot = cta_sum_fixed<T, 256>(v, red);
+        if (tid == 0) { c->rr = tot; c->ticket[0] = 0; ++c->evals; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Jacobian kernels.  All of them also produce J^T y (LS:1052) for the rows they touch: per-CTA
+// partial sums, added in CTA order by the last CTA to finish -> packed[np .. np+n).
+// ---------------------------------------------------------------------------------------------
+template <class T> struct JacArgs {
+    LargeCtl<T>* ctl;
+    const T* t; const T* yobs;
+    const T* buf0; const T* buf1;
+    T* J;
+    T* partJy;                  // gridDim.x * LARGE_NMAX
+    long long rows;
+};
+
+template <class T, int NT>
+__device__ __forceinline__ void large_finish_jy(LargeCtl<T>* c, T* partJy, const T* myJy /* smem, ldj */, int ldj, unsigned* ticket)
+{
+    __shared__ bool lastJ;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < ldj; k += NT) partJy[(size_t)blockIdx.x * LARGE_NMAX + k] = myJy[k];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) lastJ = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (lastJ) {
+        __threadfence();
+        const int n = c->n, np = n * (n + 1) / 2;
+        for (int k = tid; k < n; k += NT) {
+            T s0 = (T)0, s1 = (T)0;
+            int b = 0;
+            for (; b + 2 <= (int)gridDim.x; b += 2) { s0 += partJy[(size_t)b * LARGE_NMAX + k]; s1 += partJy[(size_t)(b + 1) * LARGE_NMAX + k]; }
+            if (b < (int)gridDim.x) s0 += partJy[(size_t)b * LARGE_NMAX + k];
+            c->packed[np + k] = s0 + s1;
+        }
+        if (tid == 0) *ticket = 0;
+    }
+}
+
+// fresh Jacobian: analytic (LS:1011-1015) or central differences (LS:1018-1049; FD = true)
+template <class Model, class T, bool FD>
+__global__ void __launch_bounds__(256) large_jac_kernel(const JacArgs<T> a)
+{
+    LargeCtl<T>* c = a.ctl;
+    if (c->done || c->jacMode != JAC_FRESH) return;
+    constexpr int NT = 256;
+    __shared__ T sp[LARGE_NMAX], saux[LARGE_NMAX], sjy[LARGE_NMAX];
+    __shared__ T sxm[FD ? LARGE_NMAX : 1], sxp[FD ? LARGE_NMAX : 1], srt[FD ? LARGE_NMAX : 1], sam[FD ? LARGE_NMAX : 1], sap[FD ? LARGE_NMAX : 1];
+    __shared__ T st_[LARGE_TILE], sy_[LARGE_TILE], syo_[LARGE_TILE];
+    extern __shared__ __align__(16) unsigned char jac_smem[];
+    T* tile = reinterpret_cast<T*>(jac_smem);                  // LARGE_TILE x (ldj + 1)
+    const int n = c->n, ldj = c->ldj, tp = ldj + 1, tid = threadIdx.x;
+    const T* y = c->ysel ? a.buf1 : a.buf0;
+
+    for (int k = tid; k < n; k += NT) {
+        const T v = c->x[k]; sp[k] = v; saux[k] = Model::aux_of(k, n, v);
+        if (FD) {                                                                                  // LS:1026-1033
+            T xmh = v - c->st.jacobianEpsilon, xph = v + c->st.jacobianEpsilon;
+            xmh = t_max(xmh, c->l[k]); xph = t_min(xph, c->u[k]);
+            const T twh = xph - xmh;
+            sxm[k] = xmh; sxp[k] = xph; srt[k] = (twh != (T)0) ? rcp_ni(twh) : (T)0;               // rt == 0 marks "column = 0" (LS:1045-1047)
+            sam[k] = Model::aux_of(k, n, xmh); sap[k] = Model::aux_of(k, n, xph);
+        }
+    }
+    for (int k = tid; k < LARGE_NMAX; k += NT) sjy[k] = (T)0;
+    for (int e = tid; e < LARGE_TILE * tp; e += NT) tile[e] = (T)0;          // pad column (ldj > n) stays 0
+    __syncthreads();
+
+    const long long tiles = (a.rows + LARGE_TILE - 1) / LARGE_TILE;
+    const long long per = (tiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = (t0 + per < tiles) ? t0 + per : tiles;
+    const int items = FD ? n : Model::jac_items(n);
+    T myJy = (T)0;                                             // thread k < ldj owns column k
+
+    for (long long tl = t0; tl < t1; ++tl) {
+        const long long row0 = tl * LARGE_TILE;
+        if (tid < LARGE_TILE) {
+            const long long row = row0 + tid;
+            const bool ok = row < a.rows;
+            st_[tid] = ok ? a.t[row] : (T)0;
+            sy_[tid] = ok ? y[row] : (T)0;
+            if (FD) syo_[tid] = ok ? a.yobs[row] : (T)0;
+        }
+        __syncthreads();
+        for (int w = tid; w < LARGE_TILE * items; w += NT) {
+            const int r = w / items, item = w - r * items;
+            if (row0 + r >= a.rows) continue;
+            if (!FD) {
+                ParamView<T> pv{sp, saux, -1, (T)0, (T)0};
+                Model::jac_item(pv, n, item, st_[r], tile + r * tp);
+            } else {
+                T v = (T)0;
+                if (srt[item] != (T)0) {
+                    ParamView<T> pp{sp, saux, item, sxp[item], sap[item]};
+                    ParamView<T> pm{sp, saux, item, sxm[item], sam[item]};
+                    const T fp = Model::residual(pp, n, st_[r], syo_[r]);
+                    const T fm = Model::residual(pm, n, st_[r], syo_[r]);
+                    v = (fp - fm) * srt[item];                                                     // LS:1040-1042
+                }
+                tile[r * tp + item] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < ldj) {
+            T acc = myJy;
+#pragma unroll 8
+            for (int r = 0; r < LARGE_TILE; ++r) acc += tile[r * tp + tid] * sy_[r];
+            myJy = acc;
+        }
+        for (int e = tid; e < LARGE_TILE * ldj; e += NT) {
+            const int r = e / ldj, k = e - r * ldj;
+            if (row0 + r < a.rows) a.J[(size_t)(row0 + r) * ldj + k] = tile[r * tp + k];
+        }
+        __syncthreads();
+    }
+    if (tid < ldj) sjy[tid] = myJy;
+    __syncthreads();
+    large_finish_jy<T, NT>(c, a.partJy, sjy, ldj, &c->ticket[1]);
+}
+
+// Broyden rank-1 update (LS:1001-1006), one warp per row, fused with J^T y.  UPDATE = false only
+// forms J^T y of a Jacobian that is already in memory (host-callback mode after the user's g).
+//   mBuffer = f_old, y = f_new:   v = ((f_old - f_new) + J dX) * (-1/||dX||^2);   J += v dX^T
+template <class T, bool UPDATE>
+__global__ void __launch_bounds__(256) large_broyden_kernel(const JacArgs<T> a)
+{
+    LargeCtl<T>* c = a.ctl;
+    if (c->done || c->jacMode != (UPDATE ? JAC_BROYDEN : JAC_FRESH)) return;
+    constexpr int NT = 256, NW = NT / 32, Q = LARGE_NMAX / 32;
+    __shared__ T sw[NW][LARGE_NMAX], sjy[LARGE_NMAX];
+    const int ldj = c->ldj, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T* y = c->ysel ? a.buf1 : a.buf0;
+    const T* mb = c->ysel ? a.buf0 : a.buf1;
+    T dx[Q], jy[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { const int k = lane + 32 * q; dx[q] = (UPDATE && k < c->n) ? c->dX[k] : (T)0; jy[q] = (T)0; }
+    const T negd = UPDATE ? -((T)1 / c->deltaX_dot) : (T)0;                                        // LS:1001
+
+    const long long per = (a.rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * per, r1 = (r0 + per < a.rows) ? r0 + per : a.rows;
+    for (long long row = r0 + warp; row < r1; row += NW) {
+        T* Jr = a.J + (size_t)row * ldj;
+        T jv[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { const int k = lane + 32 * q; jv[q] = (k < ldj) ? Jr[k] : (T)0; }
+        const T yr = y[row];
+        if (UPDATE) {
+            T acc = (T)0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) acc += jv[q] * dx[q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            const T v = ((mb[row] - yr) + acc) * negd;                                             // LS:1003-1005
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int k = lane + 32 * q;
+                jv[q] += v * dx[q];                                                                // LS:1006
+                if (k < ldj) Jr[k] = jv[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) jy[q] += jv[q] * yr;
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) sw[warp][lane + 32 * q] = jy[q];
+    __syncthreads();
+    if (tid < LARGE_NMAX) {
+        T s = (T)0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += sw[w][tid];
+        sjy[tid] = s;
+    }
+    __syncthreads();
+    large_finish_jy<T, NT>(c, a.partJy, sjy, ldj, &c->ticket[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// control kernels (one CTA)
+// ---------------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ void large_reject(LargeCtl<T>* c)
+{
+    c->lambda *= c->st.lambdaIncrease * c->mu; c->mu *= (T)2;                                      // LS:1103-1104, 1127-1128, 1154-1155
+}
+
+// after the (all-reduced) Jacobian products: LS:1052-1110
+template <class T>
+__global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeCtl<T>* c)
+{
+    if (c->done) return;
+    constexpr int NT = LARGE_CTL_THREADS;
+    extern __shared__ __align__(16) unsigned char ctl_smem[];
+    const int n = c->n, tid = threadIdx.x;
+    CtaQPScratch<T> w;
+    w.carve(ctl_smem, n);
+    T* vec = reinterpret_cast<T*>(ctl_smem + ((CtaQPScratch<T>::bytes(n) + 15) & ~(size_t)15));
+    T* sq = vec; T* sl = vec + n; T* su = vec + 2 * n; T* sx = vec + 3 * n;
+    __shared__ int s_flag;
+
+    if (c->jacMode != JAC_NONE) {
+        const int np = n * (n + 1) / 2;
+        for (int e = tid; e < n * n; e += NT) {
+            const int i = e / n, j = e - i * n;
+            if (j <= i) c->JJ[i * LARGE_NMAX + j] = c->packed[i * (i + 1) / 2 + j];
+        }
+        for (int k = tid; k < n; k += NT) c->Jy[k] = c->packed[np + k];
+        __syncthreads();
+        if (tid == 0) {                                                                            // LS:1053-1062
+            // iamax: first index of max |.|; NaN never wins unless it is element 0 (reference BLAS behaviour)
+            T best = t_abs(c->Jy[0]); T sel = c->Jy[0];
+            for (int k = 1; k < n; ++k) { const T v = t_abs(c->Jy[k]); if (v > best) { best = v; sel = c->Jy[k]; } }
+            int f = 0;
+            if (!(t_abs(sel) > c->st.gradTolerance)) {
+                if (c->age == 0) { c->status = mir_ls_gConverged; c->done = 1; f = 1; }
+                else { c->age = c->maxAge; c->skipRest = 1; f = 1; }
+            }
+            s_flag = f;
+        }
+        __syncthreads();
+        if (s_flag) return;
+    }
+
+    if (tid == 0) {
+        if (!(c->lambda >= c->st.minLambda)) {                                                     // LS:1067-1072
+            T dmax = c->JJ[0];
+            for (int i = 1; i < n; ++i) { const T d = c->JJ[i * LARGE_NMAX + i]; if (t_abs(d) > t_abs(dmax)) dmax = d; }
+            c->lambda = (T)(0.001 * (double)dmax);
+            if (!(c->lambda >= c->st.minLambda)) c->lambda = (T)1;
+        }
+    }
+    __syncthreads();
+    const T lambda = c->lambda;
+    for (int k = tid; k < n; k += NT) { sq[k] = c->Jy[k]; sl[k] = c->l[k] - c->x[k]; su[k] = c->u[k] - c->x[k]; sx[k] = (T)0; }   // LS:1074-1077
+    __syncthreads();
+    const T* JJ = c->JJ;
+    auto P = [&](int i, int j) -> T { const T v = JJ[i * LARGE_NMAX + j]; return i == j ? v + lambda : v; };   // LS:1078-1079
+    unsigned iters = 0, solves = 0;
+    const int qs = cta_boxqp<T, NT>(c->st.qpSettings, n, P, sq, sl, su, sx, w, iters, solves);   // LS:1080
+    __syncthreads();
+    bool nan = false;                                                                              // LS:1087-1092
+    for (int k = tid; k < n; k += NT) nan = nan || !(sx[k] <= sx[k]);
+    const bool anyNan = cta_any<NT>(nan);
+    if (tid == 0) {
+        c->qpSolves += solves; c->qpIters += iters;
+        int f = 0;
+        if (qs != mir_qp_solved || anyNan) { c->status = mir_ls_numericError; c->done = 1; f = 1; }   // LS:1080-1092
+        s_flag = f;
+    }
+    __syncthreads();
+    if (s_flag) return;
+
+    for (int k = tid; k < n; k += NT) {                                                            // LS:1096-1097
+        const T xk = c->x[k];
+        const T d = add_rn(add_rn(sx[k], xk), -xk);
+        sx[k] = d; c->dX[k] = d;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        T nd = (T)0;                                                                               // LS:1099
+        for (int k = 0; k < n; ++k) nd += sx[k] * sx[k];
+        c->nd = nd;
+        if (!(sqrt_ni(nd) < c->st.maxStep)) { large_reject(c); c->skipRest = 1; }                  // LS:1101-1106
+        else {
+            bool same = true;                                                                      // LS:1108-1110
+            for (int k = 0; k < n; ++k) {
+                const T xk = c->x[k];
+                const T v = t_max(t_min(add_rn(sx[k], xk), c->u[k]), c->l[k]);
+                c->xt[k] = v;
+                same = same && (v == xk) && (signbit(v) == signbit(xk));
+            }
+            ++c->fCalls;                                                                           // LS:1112
+            c->doEval = same ? 0 : 1;      // f(xt) == y bit for bit when xt == x: the evaluation is skipped, trial = residual
+            if (same) c->rr = c->residual;
+        }
+    }
+}
+
+// after the (all-reduced) trial residual: LS:1117-1175, then the guards of the next pass
+template <class T>
+__global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(LargeCtl<T>* c)
+{
+    if (c->done) return;
+    constexpr int NT = LARGE_CTL_THREADS;
+    __shared__ T sdx[LARGE_NMAX], sjy[LARGE_NMAX], red[NT / 32];
+    __shared__ int s_go;
+    const int n = c->n, tid = threadIdx.x;
+
+    if (c->initPhase) {                                                                            // LS:953-971
+        if (tid == 0) {
+            c->initPhase = 0;
+            c->residual = c->rr; c->ysel ^= 1; c->fCalls = 1;
+            c->fConverged = (c->residual <= c->st.maxGoodResidual) ? 1 : 0;
+            c->needJacobian = 1; c->age = c->maxAge; c->lambda = (T)0; c->iterations = 0; c->mu = (T)1;
+            c->status = mir_ls_maxIterations; c->deltaX_dot = (T)0;
+            large_begin_pass(c);
+        }
+        return;
+    }
+
+    if (tid == 0) {
+        int go = 0;
+        if (!c->skipRest) {
+            const T trial = c->rr;
+            if (!(trial <= Num<T>::inf())) { c->status = mir_ls_numericError; c->done = 1; }       // LS:1117-1122
+            else {
+                const T improvement = c->residual - trial;                                         // LS:1124
+                if (!(improvement > (T)0)) large_reject(c);                                        // LS:1125-1130
+                else go = 1;
+            }
+        }
+        s_go = go;
+    }
+    __syncthreads();
+    if (s_go) {
+        // accepted: LS:1132-1139
+        for (int k = tid; k < n; k += NT) { c->x[k] = c->xt[k]; sdx[k] = c->dX[k]; }
+        __syncthreads();
+        // symv(Lower, 1, JJ, deltaX, 2, Jy) with the undamped JJ, then pred = -Jy . deltaX          LS:1141-1142
+        for (int i = tid; i < n; i += NT) {
+            T acc = (T)0;
+            for (int j = 0; j < n; ++j) acc += ((i >= j) ? c->JJ[i * LARGE_NMAX + j] : c->JJ[j * LARGE_NMAX + i]) * sdx[j];
+            const T v = acc + (T)2 * c->Jy[i];
+            c->Jy[i] = v; sjy[i] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const T improvement = c->residual - c->rr;
+            c->needJacobian = 1; c->mu = (T)1; ++c->iterations; ++c->accepted; c->ysel ^= 1;
+            c->residual = c->rr;
+            c->fConverged = (c->residual <= c->st.maxGoodResidual) ? 1 : 0;
+            c->deltaX_dot = c->nd;
+            T pred = (T)0;
+            for (int k = 0; k < n; ++k) pred += sjy[k] * sdx[k];
+            pred = -pred;
+            if (!(pred > (T)0)) { c->status = mir_ls_furtherImprovement; c->done = 1; }            // LS:1144-1148
+            else {
+                const T rho = div_ni(pred, improvement);                                           // LS:1150
+                if (rho < c->st.minStepQuality) large_reject(c);                                   // LS:1152-1156
+                else if (rho >= c->st.goodStepQuality) c->lambda = t_max(c->st.lambdaDecrease * c->lambda * c->mu, c->st.minLambda);   // LS:1158-1161
+                // LS:1164: !(sqrt(dd) > absTol && nrm2(x) > sqrt(dd) * relTol)
+                T xmax = (T)0;
+                for (int k = 0; k < n; ++k) xmax = t_max(xmax, t_abs(c->x[k]));
+                T xn = (T)0;
+                if (xmax > (T)0) {
+                    const T inv = rcp_ni(xmax);
+                    T ss = (T)0;
+                    for (int k = 0; k < n; ++k) { const T v = c->x[k] * inv; ss += v * v; }
+                    xn = xmax * sqrt_ni(ss);
+                }
+                const T sd = sqrt_ni(c->deltaX_dot);
+                if (!(sd > c->st.absTolerance && xn > sd * c->st.relTolerance)) {                  // LS:1164-1173
+                    if (c->age == 0) { c->status = mir_ls_xConverged; c->done = 1; }
+                    else c->age = c->maxAge;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && !c->done) {
+        if (!(c->iterations < c->st.maxIterations)) { c->status = mir_ls_maxIterations; c->done = 1; }   // LS:1175
+        else large_begin_pass(c);
+    }
+    (void)red;
+}
+
+}  // namespace mirb200

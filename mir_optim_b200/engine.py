@@ -148,6 +148,73 @@ class Engine(ReferenceAPI):
                                                                       _vp(iterations), C.c_void_p(stream))
         self._check(rc)
 
+    # -- one problem through the reference's own entry point, residual model on the device ------
+    def optimize_device_model(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
+                              t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
+                              fd_jacobian: bool = False):
+        """mir_optimize_least_squares_{d,s} (least_squares.d:705-748) with f = mir_b200_device_model_*:
+        the whole solve, residuals included, runs on the GPU.  x (n,) in/out.  Returns the Result POD."""
+        sfx, real, S, R, Sl, FT, _ = _types(x.dtype)
+        assert isinstance(settings, S) and x.ndim == 1 and x.flags.c_contiguous
+        n = x.shape[0]
+        if y is not None:
+            y = np.ascontiguousarray(y, dtype=x.dtype).reshape(-1); m = y.shape[0] if m is None else m
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=x.dtype).reshape(-1)
+        l = np.ascontiguousarray(l, dtype=x.dtype); u = np.ascontiguousarray(u, dtype=x.dtype)
+        desc = ModelDesc(int(model), 0, _vp(t), _vp(y))
+        f_ptr = C.cast(getattr(self.lib, f"mir_b200_device_model_{sfx}"), C.c_void_p)
+        g_ptr = None if fd_jacobian else C.cast(getattr(self.lib, f"mir_b200_device_model_jac_{sfx}"), C.c_void_p)
+        fn = getattr(self.lib, f"mir_optimize_least_squares_{sfx}")
+        res = fn(C.byref(settings), m, n, x.ctypes.data_as(C.POINTER(real)), l.ctypes.data_as(C.POINTER(real)),
+                 u.ctypes.data_as(C.POINTER(real)), Sl(0, None), _abi.SliceI(0, None),
+                 C.cast(C.pointer(desc), C.c_void_p), f_ptr, None, g_ptr, None, None)
+        if res.status == _abi.LeastSquaresStatus.numericError and self.lib.mir_b200_last_error():
+            raise B200Error(-1, self.lib.mir_b200_last_error().decode())
+        return res
+
+    # -- one large problem, rows sharded over ranks -------------------------------------------
+    def optimize_sharded(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray, t, y,
+                         comm=None, fd_jacobian: bool = False, want_stats: bool = False, stream=None):
+        """t, y: torch CUDA tensors with THIS rank's rows.  x (n,) host, identical on every rank, in/out.
+        comm: handle from :meth:`nccl_comm_init` (None = single GPU, no collective).  Blocking."""
+        import torch
+        assert isinstance(settings, _abi.LeastSquaresSettingsD) and x.dtype == np.float64 and x.ndim == 1
+        assert t.dtype == torch.float64 and y.dtype == torch.float64 and t.is_cuda and y.is_cuda
+        n = x.shape[0]
+        l = np.ascontiguousarray(l, dtype=np.float64); u = np.ascontiguousarray(u, dtype=np.float64)
+        desc = ModelDesc(int(model), MODEL_FD_JACOBIAN if fd_jacobian else 0, _vp(t), _vp(y))
+        res = _abi.LeastSquaresResultD()
+        stats = BatchStats() if want_stats else None
+        if stream is None:
+            stream = torch.cuda.current_stream(t.device).cuda_stream
+        rc = self.lib.mir_optimize_least_squares_sharded_d(C.byref(settings), C.byref(desc), t.shape[0], n, _vp(x), _vp(l), _vp(u),
+                                                           comm, C.c_void_p(stream), C.byref(res),
+                                                           C.byref(stats) if stats is not None else None)
+        self._check(rc)
+        return res, (stats.as_dict() if stats is not None else None)
+
+    def syrk_lower_device(self, J, n: int, packed, stream=None):
+        """packed[tri(i,j)] = (J^T J)[i][j], i >= j; J: (rows, ldj) float64 CUDA tensor, rows % 32 == 0.  Asynchronous."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(J.device).cuda_stream
+        self._check(self.lib.mir_b200_syrk_lower_dev_d(_vp(J), J.shape[0], n, J.shape[1], _vp(packed), C.c_void_p(stream)))
+
+    # -- NCCL bootstrap (the library binds NCCL at run time) -----------------------------------
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.mir_b200_nccl_unique_id(buf))
+        return buf.raw
+
+    def nccl_comm_init(self, nranks: int, unique_id: bytes, rank: int):
+        comm = C.c_void_p()
+        self._check(self.lib.mir_b200_nccl_comm_init(C.byref(comm), nranks, C.c_char_p(unique_id), rank))
+        return comm
+
+    def nccl_comm_destroy(self, comm):
+        self._check(self.lib.mir_b200_nccl_comm_destroy(comm))
+
     @staticmethod
     def results_from_bytes(buf, dtype) -> np.ndarray:
         """uint8 torch tensor (device or host) -> structured numpy array of Result PODs."""
