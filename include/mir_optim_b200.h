@@ -239,7 +239,9 @@ typedef enum mir_model_id {
 
 enum {
     MIR_MODEL_FD_JACOBIAN      = 1u,  /* g == null semantics: central differences, maxAge default 2n */
-    MIR_MODEL_GRID_PER_PROBLEM = 2u   /* t has batch*m entries instead of m shared ones              */
+    MIR_MODEL_GRID_PER_PROBLEM = 2u,  /* t has batch*m entries instead of m shared ones              */
+    MIR_MODEL_NO_TAIL_SHORTCUT = 4u   /* verification only: execute every pass of the lambda-overflow tail
+                                         instead of fast-forwarding it (results are identical) */
 };
 
 typedef struct mir_model_desc {

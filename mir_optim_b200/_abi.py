@@ -50,6 +50,7 @@ class ModelId(enum.IntEnum):
 
 MODEL_FD_JACOBIAN = 1
 MODEL_GRID_PER_PROBLEM = 2
+MODEL_NO_TAIL_SHORTCUT = 4
 
 
 def _settings_types(real):

@@ -169,13 +169,14 @@ template <class T> static void fd_task(mir_ls_task task, unsigned, unsigned, uns
 // the engine
 // ---------------------------------------------------------------------------------------------
 template <class T>
-static int large_solve(const typename Num<T>::Settings& st, unsigned model, bool fdJacobian, long long rows, size_t n_,
+static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsigned modelFlags, long long rows, size_t n_,
                        const T* d_t, const T* d_yobs, const HostCallbacks<T>* cb,
                        T* x, const T* l, const T* u, void* comm, cudaStream_t stream,
                        typename Num<T>::Result* result, mir_batch_stats* stats)
 {
     using Ctl = LargeCtl<T>;
     constexpr bool kDouble = std::is_same<T, double>::value;
+    const bool fdJacobian = (modelFlags & MIR_MODEL_FD_JACOBIAN) != 0;
     result->status = mir_ls_numericError; result->iterations = 0; result->fCalls = 0; result->gCalls = 0;
     result->residual = Num<T>::inf(); result->lambda = 0;
     if (stats) std::memset(stats, 0, sizeof *stats);
@@ -232,6 +233,7 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, bool
     std::unique_ptr<Ctl> h(new Ctl);
     std::memset(h.get(), 0, sizeof(Ctl));
     h->st = st; h->n = n; h->ldj = ldj; h->hasG = hasG ? 1 : 0;
+    h->tailShortcut = (modelFlags & MIR_MODEL_NO_TAIL_SHORTCUT) ? 0 : 1;
     h->maxAge = st.maxAge ? st.maxAge : (hasG ? 3u : 2u * (unsigned)n);                           // LS:945
     h->status = mir_ls_maxIterations; h->residual = Num<T>::inf();
     h->initPhase = 1; h->doEval = 1; h->ysel = 0; h->mu = 1;
@@ -383,7 +385,7 @@ static typename Num<T>::Result legacy_entry(const typename Num<T>::Settings* set
         if (!desc) { set_error("mir_optim_b200: device-model mode needs fContext = mir_model_desc*"); return ret; }
         if (g && (void*)g != Sentinels<T>::g()) { set_error("mir_optim_b200: device-model mode takes g = NULL (finite differences) or mir_b200_device_model_jac_*"); return ret; }
         mir_model_desc d = *desc;
-        d.flags = (d.flags & ~(uint32_t)(MIR_MODEL_FD_JACOBIAN | MIR_MODEL_GRID_PER_PROBLEM)) | (g ? 0u : (uint32_t)MIR_MODEL_FD_JACOBIAN);
+        d.flags = (d.flags & (uint32_t)MIR_MODEL_NO_TAIL_SHORTCUT) | (g ? 0u : (uint32_t)MIR_MODEL_FD_JACOBIAN);
         // small shapes: the register-resident kernel (one warp for the whole problem)
         int rc = batched_host_entry<T>(settings, &d, 1, m, n, x, l, u, 0, &ret, nullptr, -1);
         if (rc == MIR_B200_OK) return ret;
@@ -399,7 +401,7 @@ static typename Num<T>::Result legacy_entry(const typename Num<T>::Settings* set
         }
         if (m && d.t) cudaMemcpyAsync(dt, d.t, sizeof(T) * m, cudaMemcpyHostToDevice, stream);
         if (m && d.y) cudaMemcpyAsync(dy, d.y, sizeof(T) * m, cudaMemcpyHostToDevice, stream);
-        rc = large_solve<T>(*settings, d.model, g == nullptr, (long long)m, n, dt, dy, nullptr, x, l, u, nullptr, stream, &ret, nullptr);
+        rc = large_solve<T>(*settings, d.model, d.flags, (long long)m, n, dt, dy, nullptr, x, l, u, nullptr, stream, &ret, nullptr);
         cudaFreeAsync(dt, stream); cudaFreeAsync(dy, stream);
         cudaStreamSynchronize(stream); cudaStreamDestroy(stream);
         if (rc) ret.status = mir_ls_numericError;
@@ -417,7 +419,7 @@ static typename Num<T>::Result legacy_entry(const typename Num<T>::Settings* set
     if (require_device(-1)) return ret;
     cudaStream_t stream = nullptr;
     if (check_cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return ret;
-    const int rc = large_solve<T>(*settings, 0, g == nullptr, (long long)m, n, nullptr, nullptr, &cb, x, l, u, nullptr, stream, &ret, nullptr);
+    const int rc = large_solve<T>(*settings, 0, g ? 0u : (unsigned)MIR_MODEL_FD_JACOBIAN, (long long)m, n, nullptr, nullptr, &cb, x, l, u, nullptr, stream, &ret, nullptr);
     cudaStreamSynchronize(stream); cudaStreamDestroy(stream);
     if (rc) ret.status = mir_ls_numericError;
     return ret;
@@ -458,7 +460,7 @@ int mir_optimize_least_squares_sharded_d(const mir_least_squares_settings_d* set
     clear_error();
     if (!settings || !model || !x || !l || !u || !result) { set_error("mir_optim_b200: null argument"); return MIR_B200_EINVAL; }
     if (m_local && (!model->t || !model->y)) { set_error("mir_optim_b200: sharded solve needs device pointers model->t / model->y"); return MIR_B200_EINVAL; }
-    return large_solve<double>(*settings, model->model, (model->flags & MIR_MODEL_FD_JACOBIAN) != 0, (long long)m_local, n,
+    return large_solve<double>(*settings, model->model, model->flags, (long long)m_local, n,
                                (const double*)model->t, (const double*)model->y, nullptr, x, l, u, nccl_comm, (cudaStream_t)cuda_stream,
                                result, stats);
 }

@@ -41,6 +41,7 @@ template <class T> struct LargeCtl {
     int n, ldj;
     unsigned maxAge;
     int hasG;                    // analytic Jacobian supplied (g != null)
+    int tailShortcut;            // fast-forward the inert lambda-overflow tail (lm_small.cuh, tail_is_inert)
     // loop state, LS:959-971
     T lambda, mu, residual, deltaX_dot, nd;
     unsigned age, iterations, fCalls, gCalls;
@@ -84,6 +85,20 @@ template <class T> __device__ void large_begin_pass(LargeCtl<T>* c)
     bool nan = false;                                                                              // LS:990-995
     for (int i = 0; i < c->n; ++i) nan = nan || !(c->x[i] <= c->x[i]);
     if (nan) { c->status = mir_ls_numericError; c->done = 1; return; }
+    if (!c->needJacobian && c->age == 0 && c->tailShortcut) {
+        // inert lambda-overflow tail (proof at tail_is_inert in lm_small.cuh): replay the scalar recurrence only
+        T q2 = (T)0, xmin = Num<T>::inf();
+        for (int i = 0; i < c->n; ++i) { q2 += c->Jy[i] * c->Jy[i]; xmin = t_min(xmin, t_abs(c->x[i])); }
+        if (xmin > (T)0 && sqrt_ni(q2) < c->lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125))) {
+            for (;;) {
+                ++c->fCalls;
+                c->lambda *= c->st.lambdaIncrease * c->mu; c->mu *= (T)2;
+                ++c->passes;
+                if (!(c->lambda <= c->st.maxLambda)) break;
+            }
+            c->status = mir_ls_furtherImprovement; c->done = 1; return;
+        }
+    }
     if (c->needJacobian) {                                                                         // LS:996-998
         c->needJacobian = 0;
         if (c->age < c->maxAge) { ++c->age; c->jacMode = JAC_BROYDEN; ++c->broyden; }              // LS:999-1007

@@ -16,6 +16,8 @@
 //     pass, LS:1065; with unchanged J it returns the same matrix).
 //   * If the trial point equals x bit for bit, f(trial) == y and trial residual == residual, so
 //     the pass is a rejection (LS:1124-1130); the model evaluation is skipped, fCalls still counts it.
+//   * The lambda-overflow tail (the reference's normal exit on noisy data, LS:979-983 + 1125-1130) is
+//     fast-forwarded once it is provably inert -- see tail_is_inert() below.
 #pragma once
 #include "boxqp_small.cuh"
 #include "models.cuh"
@@ -41,6 +43,25 @@ struct SmallBatchArgs {
 #define MIRB200_MINBLOCKS 1
 #endif
 
+// Lambda-overflow tail.  State: J is current (needJacobian == false), age == 0, the last pass was a rejection.
+// The step solves min 1/2 d'Pd + q'd over a box that contains d = 0, with P = J'J + lambda I >= lambda I and
+// q = J'r.  The minimiser has objective <= 0, hence lambda/2 |d|^2 <= -q'd <= |q| |d| and |d|_2 <= 2 |q|_2 / lambda.
+// Once 2 |q|_2 / lambda < 1/4 min_i ulp(x_i) (all x_i != 0; ulp(x) >= |x| eps/2, and the factor 4 covers the
+// O(eps) relative error of the computed solution of this perfectly conditioned system and the half-width binade
+// just below a power of two), every component of (d + x) - x (LS:1096-1097) is exactly 0, so the trial point is x,
+// the trial residual equals the residual bit for bit and the pass is a rejection: lambda *= lambdaIncrease * mu,
+// mu *= 2 (LS:1125-1130).  Nothing else changes (age == 0, so `mu > 16` cannot force a new Jacobian, LS:984-989),
+// |q| / lambda only shrinks, and the same holds for every later pass until !(lambda <= maxLambda) ends the run with
+// furtherImprovement (LS:979-983).  The caller therefore replays only the scalar recurrence (fCalls, lambda, mu).
+template <class T, int N>
+__device__ __forceinline__ bool tail_is_inert(const T (&x)[N], const T (&Jy)[N], T lambda)
+{
+    T q2 = (T)0, xmin = Num<T>::inf();
+#pragma unroll
+    for (int i = 0; i < N; ++i) { q2 += Jy[i] * Jy[i]; xmin = t_min(xmin, t_abs(x[i])); }
+    return xmin > (T)0 && sqrt_ni(q2) < lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125));
+}
+
 template <class Model, class T, int LANES, int R, bool FD>
 __global__ void __launch_bounds__(128, MIRB200_MINBLOCKS)
 lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
@@ -58,6 +79,7 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
     const int m = (int)args.m;
     constexpr bool useFD = FD;        // g == null semantics (finite differences), compile-time to keep the code small
     const bool gridPerProblem = (args.flags & MIR_MODEL_GRID_PER_PROBLEM) != 0;
+    const bool tailShortcut = (args.flags & MIR_MODEL_NO_TAIL_SHORTCUT) == 0;
     const T* __restrict__ tptr = static_cast<const T*>(args.t);
     const T* __restrict__ yptr = static_cast<const T*>(args.y);
 
@@ -286,6 +308,18 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         age = maxAge;
                         continue;
                     }
+                }
+
+                if (age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, lambda)) {
+                    // (needJacobian is false here.)  Replay the rejections: LS:1112, 1125-1130, then the next pass's LS:979-983.
+                    for (;;) {
+                        ++ret.fCalls;
+                        lambda *= st.lambdaIncrease * mu; mu *= (T)2;
+                        ++sPasses;
+                        if (!(lambda <= st.maxLambda)) break;
+                    }
+                    status = mir_ls_furtherImprovement;
+                    break;
                 }
 
                 if (!(lambda >= st.minLambda)) {                                             // LS:1067-1072

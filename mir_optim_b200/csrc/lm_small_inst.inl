@@ -15,6 +15,20 @@ int launch_small_model<REAL>(unsigned model, size_t n, const Num<REAL>::Settings
         set_error("mir_optim_b200: model expects n = " + std::to_string(want) + ", got " + std::to_string(n));
         return (int)MIR_B200_EINVAL;
     };
+    if (use_thread_per_problem(args.batch)) {
+        switch (model) {
+        case MIR_MODEL_EXPDECAY2:  if (n != 2) return bad_n(2); return launch_tpp<ModelExpDecay2<T, true>, T>(st, args, stream);
+        case MIR_MODEL_EXPTAU3:    if (n != 3) return bad_n(3); return launch_tpp<ModelExpTau3<T, true>, T>(st, args, stream);
+        case MIR_MODEL_EXPDECAY3:  if (n != 3) return bad_n(3); return launch_tpp<ModelExpDecay3<T, true>, T>(st, args, stream);
+        case MIR_MODEL_GAUSS4:     if (n != 4) return bad_n(4); return launch_tpp<ModelGauss4<T, true>, T>(st, args, stream);
+        case MIR_MODEL_SUMEXP:
+            if (n == 4) return launch_tpp<ModelSumExp<T, 4, true>, T>(st, args, stream);
+            // n = 8: the per-thread state (36-entry packed J^T J + factor, 8 KB of Jacobian) spills and the slab
+            // traffic dominates -- measured 4x slower than the lane-group kernel on B200, which therefore keeps it
+            break;
+        default: break;      // data-free two-row models: the group kernel below
+        }
+    }
     switch (model) {
     case MIR_MODEL_LINEAR2:    if (n != 2) return bad_n(2); return launch_small<ModelLinear2<T>, T, 32, 1>(st, args, stream);
     case MIR_MODEL_ROSENBROCK: if (n != 2) return bad_n(2); return launch_small<ModelRosenbrock<T>, T, 32, 1>(st, args, stream);

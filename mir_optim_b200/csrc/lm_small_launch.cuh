@@ -1,7 +1,10 @@
 // lm_small_launch.cuh -- host-side launcher for lm_small_kernel: picks the rows-per-lane
 // instantiation from m, sizes a persistent grid (a multiple of the SM count) and enqueues.
 #pragma once
+#include <cstdlib>
+#include <cstring>
 #include "lm_small.cuh"
+#include "lm_tpp.cuh"
 #include "runtime.cuh"
 
 namespace mirb200 {
@@ -27,6 +30,52 @@ int launch_small_one(const typename Num<T>::Settings& st, const SmallBatchArgs& 
 {
     return (args.flags & MIR_MODEL_FD_JACOBIAN) ? launch_small_fd<Model, T, LANES, R, true>(st, args, stream)
                                                 : launch_small_fd<Model, T, LANES, R, false>(st, args, stream);
+}
+
+// Thread-per-problem kernel (lm_tpp.cuh): any m; used for large batches, where one thread per problem fills the GPU.
+template <class Model, class T, bool FD, bool YOS>
+int launch_tpp_cfg(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    auto kern = lm_tpp_kernel<Model, T, FD, YOS>;
+    int blocksPerSM = 0;
+    const size_t mPad = ((size_t)args.m + 1) & ~(size_t)1;
+    const size_t smem = sizeof(T) * (mPad + (YOS ? (size_t)args.m * TPP_THREADS : 0));     // shared abscissa (+ observations)
+    if (smem > 200 * 1024) { set_error("mir_optim_b200: m too large for the thread-per-problem kernel"); return MIR_B200_EUNSUPPORTED; }
+    if (smem > 48 * 1024) MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, TPP_THREADS, smem));
+    if (blocksPerSM < 1) blocksPerSM = 1;
+    unsigned long long blocksWanted = (args.batch + TPP_THREADS - 1) / TPP_THREADS;
+    unsigned long long grid = (unsigned long long)sm_count() * blocksPerSM;
+    if (blocksWanted < grid) grid = blocksWanted ? blocksWanted : 1;
+    const size_t perThread = (size_t)args.m * (Model::N + (YOS ? 2 : 3));
+    T* slab = nullptr;
+    MIRB200_CUDA(cudaMallocAsync((void**)&slab, sizeof(T) * (perThread ? perThread : 1) * TPP_THREADS * grid, stream));
+    kern<<<(unsigned)grid, TPP_THREADS, smem, stream>>>(st, args, slab);
+    count_launch();
+    const int rc = check_cuda(cudaGetLastError(), "lm_tpp_kernel launch");
+    cudaFreeAsync(slab, stream);
+    return rc;
+}
+template <class Model, class T, bool FD>
+int launch_tpp_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    // observations in shared memory while two CTAs per SM still fit (m * 128 threads * sizeof(T) <= ~100 KB)
+    const bool yos = Model::kHasData && sizeof(T) * (size_t)args.m * TPP_THREADS <= 100 * 1024;
+    return yos ? launch_tpp_cfg<Model, T, FD, true>(st, args, stream) : launch_tpp_cfg<Model, T, FD, false>(st, args, stream);
+}
+template <class Model, class T>
+int launch_tpp(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    return (args.flags & MIR_MODEL_FD_JACOBIAN) ? launch_tpp_fd<Model, T, true>(st, args, stream) : launch_tpp_fd<Model, T, false>(st, args, stream);
+}
+
+// Kernel choice: one thread per problem once the batch can fill the GPU with threads, else one lane group per
+// problem (more parallelism inside each problem).  MIRB200_BATCH_KERNEL=group|thread overrides (experiments).
+inline bool use_thread_per_problem(unsigned long long batch)
+{
+    static const int forced = [] { const char* e = std::getenv("MIRB200_BATCH_KERNEL"); return !e ? 0 : (!std::strcmp(e, "thread") ? 1 : (!std::strcmp(e, "group") ? 2 : 0)); }();
+    if (forced) return forced == 1;
+    return batch >= 16384ull;
 }
 
 // Rs...: the rows-per-lane instantiations compiled for this model, ascending.

@@ -60,68 +60,68 @@ template <class T> struct ModelSqrtCircle {
 };
 
 // r_i = p0 exp(-t_i p1) - y_i                                  least_squares.d:347, 360
-template <class T> struct ModelExpDecay2 {
+template <class T, bool INL = false> struct ModelExpDecay2 {
     static constexpr int N = 2; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
-        return sub_rn(mul_rn(p[0], exp_repro(mul_rn(-t, p[1]))), y);
+        return sub_rn(mul_rn(p[0], exp_sel<INL>(mul_rn(-t, p[1]))), y);
     }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        const T e = exp_repro(mul_rn(-t, p[1]));
+        const T e = exp_sel<INL>(mul_rn(-t, p[1]));
         J[0] = e; J[1] = mul_rn(-mul_rn(p[0], t), e);
     }
 };
 
 // r_i = p0 exp(-t_i / p1) + p2 - y_i                           least_squares.d:378, 390
-template <class T> struct ModelExpTau3 {
+template <class T, bool INL = false> struct ModelExpTau3 {
     static constexpr int N = 3; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
-        return sub_rn(add_rn(mul_rn(p[0], exp_repro(div_ni(-t, p[1]))), p[2]), y);
+        return sub_rn(add_rn(mul_rn(p[0], exp_sel<INL>(div_ni(-t, p[1]))), p[2]), y);
     }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        const T e = exp_repro(div_ni(-t, p[1]));
+        const T e = exp_sel<INL>(div_ni(-t, p[1]));
         J[0] = e; J[1] = div_ni(mul_rn(mul_rn(p[0], e), t), mul_rn(p[1], p[1])); J[2] = (T)1;
     }
 };
 
 // r_i = p0 exp(-p1 t_i) + p2 - y_i                             BASELINE configs[0]
-template <class T> struct ModelExpDecay3 {
+template <class T, bool INL = false> struct ModelExpDecay3 {
     static constexpr int N = 3; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
-        return sub_rn(add_rn(mul_rn(p[0], exp_repro(mul_rn(-p[1], t))), p[2]), y);
+        return sub_rn(add_rn(mul_rn(p[0], exp_sel<INL>(mul_rn(-p[1], t))), p[2]), y);
     }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        const T e = exp_repro(mul_rn(-p[1], t));
+        const T e = exp_sel<INL>(mul_rn(-p[1], t));
         J[0] = e; J[1] = mul_rn(-mul_rn(p[0], t), e); J[2] = (T)1;
     }
 };
 
 // Gaussian peak on a baseline: r_i = A exp(-(t_i - mu)^2 / (2 sigma^2)) + c - y_i, p = (A, mu, sigma, c)
 //                                                             BASELINE configs[1]
-template <class T> struct ModelGauss4 {
+template <class T, bool INL = false> struct ModelGauss4 {
     static constexpr int N = 4; static constexpr bool kHasData = true;
     struct Pre { T is; };
     __device__ static Pre prepare(const T (&p)[N]) { return {rcp_ni(p[2])}; }
     __device__ static T residual(const Pre& q, const T (&p)[N], int, T t, T y) {
         const T z = mul_rn(sub_rn(t, p[1]), q.is);
-        return sub_rn(add_rn(mul_rn(p[0], exp_repro(mul_rn((T)-0.5, mul_rn(z, z)))), p[3]), y);
+        return sub_rn(add_rn(mul_rn(p[0], exp_sel<INL>(mul_rn((T)-0.5, mul_rn(z, z)))), p[3]), y);
     }
     __device__ static void jacobian(const Pre& q, const T (&p)[N], int, T t, T (&J)[N]) {
         const T z = mul_rn(sub_rn(t, p[1]), q.is);
         const T zz = mul_rn(z, z);
-        const T e = exp_repro(mul_rn((T)-0.5, zz));
+        const T e = exp_sel<INL>(mul_rn((T)-0.5, zz));
         const T ae = mul_rn(p[0], e);
         J[0] = e; J[1] = mul_rn(mul_rn(ae, z), q.is); J[2] = mul_rn(mul_rn(ae, zz), q.is); J[3] = (T)1;
     }
 };
 
 // Sum of exponentials: r_i = sum_k p[2k] exp(-p[2k+1] t_i) - y_i          BASELINE configs[2]
-template <class T, int N_> struct ModelSumExp {
+template <class T, int N_, bool INL = false> struct ModelSumExp {
     static constexpr int N = N_; static constexpr bool kHasData = true;
     static_assert(N_ % 2 == 0, "sum-of-exponentials has (amplitude, rate) pairs");
     using Pre = NoPre<T>;
@@ -129,13 +129,13 @@ template <class T, int N_> struct ModelSumExp {
     __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
         T acc = (T)0;
 #pragma unroll
-        for (int k = 0; k < N; k += 2) acc = add_rn(acc, mul_rn(p[k], exp_repro(mul_rn(-p[k + 1], t))));
+        for (int k = 0; k < N; k += 2) acc = add_rn(acc, mul_rn(p[k], exp_sel<INL>(mul_rn(-p[k + 1], t))));
         return sub_rn(acc, y);
     }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
 #pragma unroll
         for (int k = 0; k < N; k += 2) {
-            const T e = exp_repro(mul_rn(-p[k + 1], t));
+            const T e = exp_sel<INL>(mul_rn(-p[k + 1], t));
             J[k] = e; J[k + 1] = mul_rn(-mul_rn(p[k], t), e);
         }
     }

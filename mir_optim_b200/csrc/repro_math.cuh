@@ -21,7 +21,7 @@ namespace mirb200 {
 
 // (static: one private copy per translation unit, so the host-side stubs never collide at link time)
 
-static __device__ __noinline__ double exp_repro(double x)
+static __device__ __forceinline__ double exp_repro_inl(double x)
 {
     if (!(x > -745.2)) return (x == x) ? 0.0 : x;
     if (x > 709.782712893384) return Num<double>::inf();
@@ -47,7 +47,7 @@ static __device__ __noinline__ double exp_repro(double x)
     return ldexp(p, ki);
 }
 
-static __device__ __noinline__ float exp_repro(float x)
+static __device__ __forceinline__ float exp_repro_inl(float x)
 {
     if (!(x > -104.0f)) return (x == x) ? 0.0f : x;
     if (x > 88.72284f) return Num<float>::inf();
@@ -66,6 +66,12 @@ static __device__ __noinline__ float exp_repro(float x)
     if (ki >= -120 && ki <= 120) return __fmul_rn(p, __int_as_float((ki + 127) << 23));
     return ldexpf(p, ki);
 }
+
+static __device__ __noinline__ double exp_repro(double x) { return exp_repro_inl(x); }
+static __device__ __noinline__ float  exp_repro(float x)  { return exp_repro_inl(x); }
+// INL = true: inlined, so independent rows interleave their polynomial chains (thread-per-problem kernel);
+// INL = false: one out-of-line copy (lane-group kernel, instruction-cache bound when inlined).
+template <bool INL, class T> __device__ __forceinline__ T exp_sel(T x) { if constexpr (INL) return exp_repro_inl(x); else return exp_repro(x); }
 
 static __device__ __noinline__ double rcp_ni(double a) { return 1.0 / a; }
 static __device__ __noinline__ float  rcp_ni(float a)  { return 1.0f / a; }

@@ -22,6 +22,25 @@ int check_cuda(cudaError_t e, const char* what)
     return MIR_B200_ECUDA;
 }
 
+// Stream-ordered allocations come from the device's default pool; by default the pool hands freed memory back to
+// the OS at the next synchronisation, so every solve would pay cudaMalloc-class latency for its (multi-GB) J / sample
+// buffers again.  Keep freed blocks cached: one-time setting per device.
+static void keep_pool_cached()
+{
+    static std::atomic<unsigned long long> doneMask{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    const unsigned long long bit = 1ull << dev;
+    if (doneMask.load(std::memory_order_relaxed) & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    doneMask.fetch_or(bit, std::memory_order_relaxed);
+}
+
 int require_device(int device)
 {
     int count = 0;
@@ -34,8 +53,10 @@ int require_device(int device)
     }
     if (device >= 0) {
         if (device >= count) { set_error("mir_optim_b200: device index out of range"); return MIR_B200_EINVAL; }
-        return check_cuda(cudaSetDevice(device), "cudaSetDevice");
+        const int rc = check_cuda(cudaSetDevice(device), "cudaSetDevice");
+        if (rc) return rc;
     }
+    keep_pool_cached();
     return MIR_B200_OK;
 }
 

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import BatchStats, ModelDesc, ModelId, MODEL_FD_JACOBIAN, MODEL_GRID_PER_PROBLEM
+from ._abi import BatchStats, ModelDesc, ModelId, MODEL_FD_JACOBIAN, MODEL_GRID_PER_PROBLEM, MODEL_NO_TAIL_SHORTCUT
 from .api import ReferenceAPI, _types
 
 RESULT_DTYPES = {
@@ -56,7 +56,7 @@ class Engine(ReferenceAPI):
     # -- batched LM, host buffers -------------------------------------------------------
     def optimize_batched(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
                          t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
-                         fd_jacobian: bool = False, want_stats: bool = False, device: int = -1):
+                         fd_jacobian: bool = False, want_stats: bool = False, device: int = -1, tail_shortcut: bool = True):
         """Solve ``batch`` independent problems; x (batch, n) is updated in place.
         l/u: shape (n,) shared, or (batch, n).  Returns (results structured array, stats dict | None)."""
         sfx, real, S, R, *_ = _types(x.dtype)
@@ -65,7 +65,7 @@ class Engine(ReferenceAPI):
         batch, n = x.shape
         l = np.ascontiguousarray(l, dtype=x.dtype); u = np.ascontiguousarray(u, dtype=x.dtype)
         bound_stride = 0 if l.ndim == 1 else n
-        flags = MODEL_FD_JACOBIAN if fd_jacobian else 0
+        flags = (MODEL_FD_JACOBIAN if fd_jacobian else 0) | (0 if tail_shortcut else MODEL_NO_TAIL_SHORTCUT)
         if y is not None:
             y = np.ascontiguousarray(y, dtype=x.dtype); assert y.shape[0] == batch
             m = y.shape[1] if m is None else m
@@ -85,7 +85,7 @@ class Engine(ReferenceAPI):
 
     # -- batched LM, device-resident torch tensors ----------------------------------------
     def optimize_batched_device(self, settings, model: ModelId, x, l, u, t=None, y=None, m: int | None = None,
-                                fd_jacobian: bool = False, results=None, stats=None, stream=None):
+                                fd_jacobian: bool = False, results=None, stats=None, stream=None, tail_shortcut: bool = True):
         """All tensors are CUDA tensors on the current device; asynchronous on `stream` (default:
         torch's current stream).  `results` : uint8 tensor (batch * sizeof(Result)); `stats`: int64[8] tensor."""
         import torch
@@ -94,7 +94,7 @@ class Engine(ReferenceAPI):
         assert isinstance(settings, S) and x.is_cuda and x.is_contiguous()
         batch, n = x.shape
         bound_stride = 0 if l.dim() == 1 else n
-        flags = MODEL_FD_JACOBIAN if fd_jacobian else 0
+        flags = (MODEL_FD_JACOBIAN if fd_jacobian else 0) | (0 if tail_shortcut else MODEL_NO_TAIL_SHORTCUT)
         if y is not None:
             m = y.shape[1] if m is None else m
         if t is not None and t.dim() == 2:
@@ -151,7 +151,7 @@ class Engine(ReferenceAPI):
     # -- one problem through the reference's own entry point, residual model on the device ------
     def optimize_device_model(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
                               t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
-                              fd_jacobian: bool = False):
+                              fd_jacobian: bool = False, tail_shortcut: bool = True):
         """mir_optimize_least_squares_{d,s} (least_squares.d:705-748) with f = mir_b200_device_model_*:
         the whole solve, residuals included, runs on the GPU.  x (n,) in/out.  Returns the Result POD."""
         sfx, real, S, R, Sl, FT, _ = _types(x.dtype)
@@ -162,7 +162,7 @@ class Engine(ReferenceAPI):
         if t is not None:
             t = np.ascontiguousarray(t, dtype=x.dtype).reshape(-1)
         l = np.ascontiguousarray(l, dtype=x.dtype); u = np.ascontiguousarray(u, dtype=x.dtype)
-        desc = ModelDesc(int(model), 0, _vp(t), _vp(y))
+        desc = ModelDesc(int(model), 0 if tail_shortcut else MODEL_NO_TAIL_SHORTCUT, _vp(t), _vp(y))
         f_ptr = C.cast(getattr(self.lib, f"mir_b200_device_model_{sfx}"), C.c_void_p)
         g_ptr = None if fd_jacobian else C.cast(getattr(self.lib, f"mir_b200_device_model_jac_{sfx}"), C.c_void_p)
         fn = getattr(self.lib, f"mir_optimize_least_squares_{sfx}")
@@ -175,7 +175,7 @@ class Engine(ReferenceAPI):
 
     # -- one large problem, rows sharded over ranks -------------------------------------------
     def optimize_sharded(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray, t, y,
-                         comm=None, fd_jacobian: bool = False, want_stats: bool = False, stream=None):
+                         comm=None, fd_jacobian: bool = False, want_stats: bool = False, stream=None, tail_shortcut: bool = True):
         """t, y: torch CUDA tensors with THIS rank's rows.  x (n,) host, identical on every rank, in/out.
         comm: handle from :meth:`nccl_comm_init` (None = single GPU, no collective).  Blocking."""
         import torch
@@ -183,7 +183,7 @@ class Engine(ReferenceAPI):
         assert t.dtype == torch.float64 and y.dtype == torch.float64 and t.is_cuda and y.is_cuda
         n = x.shape[0]
         l = np.ascontiguousarray(l, dtype=np.float64); u = np.ascontiguousarray(u, dtype=np.float64)
-        desc = ModelDesc(int(model), MODEL_FD_JACOBIAN if fd_jacobian else 0, _vp(t), _vp(y))
+        desc = ModelDesc(int(model), (MODEL_FD_JACOBIAN if fd_jacobian else 0) | (0 if tail_shortcut else MODEL_NO_TAIL_SHORTCUT), _vp(t), _vp(y))
         res = _abi.LeastSquaresResultD()
         stats = BatchStats() if want_stats else None
         if stream is None:

@@ -63,14 +63,16 @@ def c3_sumexp8(batch, dtype=np.float64, seed=3, m=128, noise=0.01):
                     fd_jacobian=True)
 
 
-def c4_gaussmix(m=4_000_000, K=42, seed=4, noise=1e-3, dtype=np.float64, row_slice=None):
+def c4_gaussmix(m=4_000_000, K=42, seed=4, noise=1e-3, dtype=np.float64, row_slice=None, width=(0.3, 0.5)):
     """configs[3]: one large problem, n = 3K+2 = 128: K Gaussians on a regular grid + linear baseline.
-    row_slice=(lo, hi) generates only those rows (for row-sharded ranks) without materialising the rest."""
+    row_slice=(lo, hi) generates only those rows (for row-sharded ranks) without materialising the rest.
+    width: peak sigma range in units of the peak spacing; (0.3, 0.5) gives neighbouring peaks 2-3 sigma apart (overlapping,
+    cond(J'J) ~ 1e4): with defaults the reference algorithm takes ~37 accepted steps and ends in the lambda-overflow tail."""
     n = 3 * K + 2
     rng = np.random.default_rng(seed)
     centers = (np.arange(K) + 0.5) / K
     amps = rng.uniform(0.5, 2.0, K)
-    widths = rng.uniform(0.6, 1.0, K) / K
+    widths = rng.uniform(width[0], width[1], K) / K
     truth = np.empty(n); truth[0:3 * K:3] = amps; truth[1:3 * K:3] = centers; truth[2:3 * K:3] = widths
     truth[n - 2] = 0.3; truth[n - 1] = -0.2
     x0 = truth.copy()

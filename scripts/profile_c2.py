@@ -32,4 +32,4 @@ for _ in range(a.launches):
     res = eng.optimize_batched_device(s, wl.model, x, l, u, t=t, y=y, fd_jacobian=wl.fd_jacobian, stats=stats)
     e1.record(); torch.cuda.synchronize()
     print(f"{wl.name}: {e0.elapsed_time(e1):.2f} ms -> {a.batch / e0.elapsed_time(e1) * 1e3:.0f} fits/s")
-print(dict(zip(("problems", "passes", "accepted", "fresh", "broyden", "evals", "qp_solves", "qp_it"), stats.cpu().tolist())))
+if a.launches > 1: print(dict(zip(("problems", "passes", "accepted", "fresh", "broyden", "evals", "qp_solves", "qp_it"), stats.cpu().tolist())))

@@ -1,0 +1,36 @@
+"""Row-sharded large problem over 2 GPUs (NCCL all-reduce inside mir_optimize_least_squares_sharded_d) against the
+single-GPU run of the same problem.  Skipped on boxes with fewer than 2 GPUs."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(nproc, extra):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + nproc), os.path.join(ROOT, "scripts", "c4_sharded.py"), "--reps", "1"] + extra
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+
+
+def test_two_rank_sharded_solve_matches_one_rank():
+    import mir_optim_b200 as mo
+    if mo.engine.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    for extra in (["--rows", "100000", "--K", "10", "--max-iterations", "4", "--noise", "1e-6"], ["--rows", "100000", "--K", "10", "--noise", "1e-6"]):
+        one = _run(1, extra); two = _run(2, extra)
+        assert two["x_bit_identical_across_ranks"]
+        if "--max-iterations" in extra:
+            assert (one["status"], one["iterations"], one["fCalls"], one["gCalls"]) == (two["status"], two["iterations"], two["fCalls"], two["gCalls"])
+            assert np.max(np.abs(np.array(one["x"]) - np.array(two["x"])) / np.abs(np.array(one["x"]))) < 1e-10
+        else:
+            assert one["status"] >= 0 and two["status"] >= 0
+            assert np.max(np.abs(np.array(one["x"]) - np.array(two["x"])) / np.abs(np.array(one["x"]))) < 1e-6
+        assert abs(one["residual"] - two["residual"]) <= 1e-9 * one["residual"]
