@@ -33,13 +33,14 @@ int launch_small_one(const typename Num<T>::Settings& st, const SmallBatchArgs& 
 }
 
 // Thread-per-problem kernel (lm_tpp.cuh): any m; used for large batches, where one thread per problem fills the GPU.
-template <class Model, class T, bool FD, bool YOS>
+template <class Model, class T, bool FD, bool YOS, bool VL>
 int launch_tpp_cfg(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
-    auto kern = lm_tpp_kernel<Model, T, FD, YOS>;
+    auto kern = lm_tpp_kernel<Model, T, FD, YOS, VL>;
     int blocksPerSM = 0;
     const size_t mPad = ((size_t)args.m + 1) & ~(size_t)1;
-    const size_t smem = sizeof(T) * (mPad + (YOS ? (size_t)args.m * TPP_THREADS : 0));     // shared abscissa (+ observations)
+    // shared abscissa (+ observations) (+ the accepted steps of the v-list)
+    const size_t smem = sizeof(T) * (mPad + (YOS ? (size_t)args.m * TPP_THREADS : 0) + (VL ? (size_t)TPP_VLN * Model::N * TPP_THREADS : 0));
     if (smem > 200 * 1024) { set_error("mir_optim_b200: m too large for the thread-per-problem kernel"); return MIR_B200_EUNSUPPORTED; }
     if (smem > 48 * 1024) MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, TPP_THREADS, smem));
@@ -47,7 +48,7 @@ int launch_tpp_cfg(const typename Num<T>::Settings& st, const SmallBatchArgs& ar
     unsigned long long blocksWanted = (args.batch + TPP_THREADS - 1) / TPP_THREADS;
     unsigned long long grid = (unsigned long long)sm_count() * blocksPerSM;
     if (blocksWanted < grid) grid = blocksWanted ? blocksWanted : 1;
-    const size_t perThread = (size_t)args.m * (Model::N + (YOS ? 2 : 3));
+    const size_t perThread = (size_t)args.m * TppSlab<Model::N, YOS, VL>::ELEMS;
     T* slab = nullptr;
     MIRB200_CUDA(cudaMallocAsync((void**)&slab, sizeof(T) * (perThread ? perThread : 1) * TPP_THREADS * grid, stream));
     kern<<<(unsigned)grid, TPP_THREADS, smem, stream>>>(st, args, slab);
@@ -60,8 +61,15 @@ template <class Model, class T, bool FD>
 int launch_tpp_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
     // observations in shared memory while two CTAs per SM still fit (m * 128 threads * sizeof(T) <= ~100 KB)
-    const bool yos = Model::kHasData && sizeof(T) * (size_t)args.m * TPP_THREADS <= 100 * 1024;
-    return yos ? launch_tpp_cfg<Model, T, FD, true>(st, args, stream) : launch_tpp_cfg<Model, T, FD, false>(st, args, stream);
+    static const bool noYOS = [] { const char* e = std::getenv("MIRB200_TPP_YOS"); return e && *e == '0'; }();      // experiments
+    const bool yos = Model::kHasData && !noYOS && sizeof(T) * ((size_t)args.m + TPP_VLN * Model::N) * TPP_THREADS <= 100 * 1024;
+    if constexpr (!FD) {
+        // analytic Jacobian with the default maxAge (3, LS:945) or a smaller one: the v-list scheme (no stored Jacobian)
+        static const bool noVL = [] { const char* e = std::getenv("MIRB200_TPP_STORED_J"); return e && *e == '1'; }();
+        if ((st.maxAge ? st.maxAge : 3u) <= (unsigned)TPP_VLN && !noVL)
+            return yos ? launch_tpp_cfg<Model, T, FD, true, true>(st, args, stream) : launch_tpp_cfg<Model, T, FD, false, true>(st, args, stream);
+    }
+    return yos ? launch_tpp_cfg<Model, T, FD, true, false>(st, args, stream) : launch_tpp_cfg<Model, T, FD, false, false>(st, args, stream);
 }
 template <class Model, class T>
 int launch_tpp(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)

@@ -9,15 +9,32 @@
 //
 // Data layout.  Per thread: x, bounds, trial point, step, J^T r, packed lower J^T J, lambda/mu/age and the
 // counters live in registers.  The m-sized vectors -- observations, y (current residuals), mBuffer (trial /
-// previous residuals) and the m x n Jacobian that the Broyden update needs in place (LS:1003-1006) -- live in a
-// per-CTA slab in global memory laid out [element][thread], so the 32 problems of a warp read and write 32
-// consecutive values: every access is a fully coalesced 256-byte (double) transaction served from L1/L2.
+// previous residuals), the Broyden vector v and the m x n Jacobian that the Broyden update needs in place
+// (LS:1003-1006) -- live in a per-CTA slab in global memory laid out [element][thread], so the 32 problems of
+// a warp read and write 32 consecutive values: every access is a fully coalesced 256-byte (double) transaction.
 //
-// Lock-step state machine.  All threads of a warp walk the same phase sequence once per LM pass
-//     fetch -> guards -> Jacobian -> step (BOXCQP) -> trial evaluation -> accept/reject
-// and a phase a problem does not need this pass is predicated off, so the warp reconverges after every phase
-// instead of drifting apart; a thread that finishes its problem pulls the next index from an atomic counter
-// at the next pass boundary (pass counts vary 10x across a batch).
+// Lock-step state machine.  All threads of a warp walk the same phase sequence once per warp pass
+//     fetch -> guards -> [FD Jacobian] -> g-test -> step (BOXCQP) -> row phase -> accept/reject
+// and a phase a problem does not need is predicated off, so the warp reconverges after every phase; a thread
+// that finishes its problem pulls the next index from an atomic counter at the next pass boundary.
+//
+// ONE row loop per pass.  A separate Jacobian phase would run with a third of the lanes (only problems whose last
+// step was accepted need it; ncu, round 1: 50 % of the warp instructions at 8.7 of 32 lanes, every row iteration
+// exposing a full memory round trip).  Instead the trial evaluation f(x + delta) (LS:1113) also does, row by row
+// and SPECULATIVELY, what the next pass's Jacobian step would do if the trial is accepted:
+//   * Broyden (age < maxAge):  v = ((y_old - f_new) + J delta) * (-1/|delta|^2),  J_new = J + v delta'  (LS:999-1006)
+//   * fresh analytic Jacobian at the trial point (age == maxAge; g(x, J), LS:1011-1015) -- it shares exp() with f
+//   * J_new' f_new and J_new' J_new (LS:1052, 1065) in registers.
+// If the trial is rejected the speculative results are dropped; if it is accepted they ARE the next pass's
+// Jacobian step, operation for operation (same operands, same order), so results are bit-identical to doing it
+// afterwards.  The Jacobian in memory is updated lazily: a speculative pass stores only v; J_mem + v_p delta_p'
+// (the pending term of the last accepted step) is materialised in place by the next row pass that reads J --
+// in place is safe because the pending term belongs to an already accepted step.  A speculative FRESH Jacobian is
+// stored in place directly: with age == maxAge the old J is dead (the next Jacobian operation is a fresh one on
+// every path).  The few cases speculation cannot cover -- a forced fresh Jacobian at the current point (LS:984-989,
+// 1059-1061, 1171) -- run the same row loop in INSTALL mode (recompute f(x), bit-identical to y, and build J at x),
+// and that problem solves its QP one warp pass later.  Finite-difference fresh Jacobians (2n evaluations,
+// LS:1018-1049) keep their own phase.
 //
 // Equivalences (bit-exact w.r.t. this file's arithmetic; same as lm_small.cuh): J^T J rebuilt only when J
 // changed; trial == x skips the model evaluation; the inert lambda-overflow tail is fast-forwarded.
@@ -28,14 +45,28 @@ namespace mirb200 {
 
 constexpr int TPP_THREADS = 128;
 enum { JAC_NONE_ = 0, JAC_BROYDEN_ = 1, JAC_FRESH_ = 2 };
+enum { ROW_NONE_ = 0, ROW_EVAL_ = 1, ROW_INSTALL_ = 2 };
 
 #ifndef MIRB200_TPP_MINBLOCKS
 #define MIRB200_TPP_MINBLOCKS 1
 #endif
 
+
+// number of slab vectors of length m per thread besides the m x N Jacobian
+// (stored-J scheme: [yobs] buf0 buf1 v + m x N Jacobian;  v-list scheme: [yobs] buf0 buf1 v0 v1 v2, no Jacobian)
+constexpr int TPP_VLN = 3;          // Broyden terms the v-list scheme can hold = largest maxAge it serves
+template <int N, bool YOS, bool VL> struct TppSlab { static constexpr int ELEMS = (YOS ? 2 : 3) + (VL ? TPP_VLN : 1 + N); };
+
 // YOS: the observations of the thread's current problem live in shared memory ([row][thread], conflict-free)
 // instead of the slab -- they are read by every model evaluation, the most frequent phase.
-template <class Model, class T, bool FD, bool YOS>
+// VL ("v-list", analytic Jacobians with maxAge <= TPP_VLN only): the Jacobian is never stored.  Between two fresh
+// Jacobians at most maxAge Broyden terms exist, so the current J row is rebuilt on the fly as
+//     ((g_row(x_anchor) + v_1 d_1') + v_2 d_2') + v_3 d_3'
+// -- the same operations in the same order as the in-place updates (LS:1006), hence the same bits -- from the anchor
+// point (registers), the accepted steps d_k (shared memory) and the vectors v_k (slab).  One extra exp per row buys
+// a 3x smaller memory stream (ncu, round 1: the stored-J row loop moved 233 KB per fit and ran at 44 % of HBM
+// bandwidth with 12 % occupancy) and a slab that fits the L2.
+template <class Model, class T, bool FD, bool YOS, bool VL>
 __global__ void __launch_bounds__(TPP_THREADS, MIRB200_TPP_MINBLOCKS)
 lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* __restrict__ slabBase)
 {
@@ -54,13 +85,18 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
     extern __shared__ __align__(16) unsigned char tpp_smem[];
     T* const st_ = reinterpret_cast<T*>(tpp_smem);
 
-    // slab of this CTA: [buf0 m][buf1 m][J m*N] (+ [yobs m] first when !YOS), each element strided by NT
-    constexpr int SLAB_VECS = YOS ? 2 : 3;
-    T* const slab = slabBase + (size_t)blockIdx.x * ((size_t)m * (N + SLAB_VECS)) * NT + tid;
-    T* const pYO = YOS ? st_ + ((m + 1) & ~1) + tid : slab;
-    T* const pB0 = slab + (size_t)(SLAB_VECS - 2) * m * NT;
+    static_assert(!(VL && FD), "the v-list scheme needs an analytic Jacobian");
+    // slab of this CTA: [yobs m (only !YOS)][buf0 m][buf1 m][v m (x TPP_VLN if VL)][J m*N (not VL)], each element strided by NT
+    T* const slab = slabBase + (size_t)blockIdx.x * ((size_t)m * TppSlab<N, YOS, VL>::ELEMS) * NT + tid;
+    const int mPad = (m + 1) & ~1;
+    T* const pYO = YOS ? st_ + mPad + tid : slab;
+    T* const pB0 = slab + (size_t)(YOS ? 0 : 1) * m * NT;
     T* const pB1 = pB0 + (size_t)m * NT;
-    T* const pJ = pB1 + (size_t)m * NT;
+    T* const pV = pB1 + (size_t)m * NT;
+    T* const pJ = pV + (size_t)m * NT;                                         // (stored-J scheme only)
+    // accepted steps d_k of the v-list, [k][i][thread] in shared memory
+    T* const pDL = st_ + mPad + (YOS ? (size_t)m * NT : 0) + tid;
+    auto DL = [&](int k, int i) -> T& { return pDL[(k * N + i) * NT]; };
     auto YO = [&](int row) -> T& { return pYO[row * NT]; };
     auto JE = [&](int row, int i) -> T& { return pJ[(row * N + i) * NT]; };
 
@@ -69,19 +105,28 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
         __syncthreads();
     }
 
-    unsigned long long sPasses = 0, sAccepted = 0, sFresh = 0, sBroyden = 0, sEvals = 0, sSolves = 0, sQPIt = 0, sProblems = 0;
+    // per-thread work counters (32 bits: a thread sees far fewer than 2^32 passes per launch)
+    unsigned sPasses = 0, sAccepted = 0, sFresh = 0, sBroyden = 0, sEvals = 0, sSolves = 0, sQPIt = 0, sProblems = 0;
 
     // per-problem state
     bool active = false, retired = false, init = false;
+    bool resume = false;        // the Jacobian of this pass was just built by an INSTALL row pass: continue at the g-test
+    bool specOK = false;        // J / JJ / Jy already hold what the next Jacobian step (of kind specKind) produces
+    bool pend = false;          // stored-J: current J = J_mem + v dXp' (pending rank-1 term of the last accepted step)
+    int nterm = 0;              // v-list: Broyden terms accepted since the anchor
+    int specKind = JAC_NONE_;
     unsigned long long prob = 0;
     const T* tp = st_;
-    T x[N], lo[N], up[N], xt[N], dX[N], Jy[N], JJ[NP];
+    T x[N], xt[N], dX[N], Jy[N], JJ[NP];      // (bounds are re-read from global memory where needed)
+    T dXp[N];                   // stored-J: step of the pending term;  v-list: the anchor point of the last fresh Jacobian
+    const T* lp = static_cast<const T*>(args.l);
+    const T* upp = static_cast<const T*>(args.u);
     T lambda = (T)0, mu = (T)1, residual = Num<T>::inf(), deltaX_dot = (T)0, nd = (T)0;
     unsigned age = 0, maxAge = 1, iterations = 0, fCalls = 0, gCalls = 0;
     int status = mir_ls_numericError, ysel = 0;
     bool needJacobian = false, fConverged = false;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { x[i] = lo[i] = up[i] = xt[i] = dX[i] = Jy[i] = (T)0; }
+    for (int i = 0; i < N; ++i) { x[i] = xt[i] = dX[i] = dXp[i] = Jy[i] = (T)0; }
 #pragma unroll
     for (int i = 0; i < NP; ++i) JJ[i] = (T)0;
 
@@ -93,16 +138,16 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
             else {
                 prob = idx; ++sProblems;
                 const T* xp = static_cast<const T*>(args.x) + prob * N;
-                const T* lp = static_cast<const T*>(args.l) + prob * args.bound_stride;
-                const T* upp = static_cast<const T*>(args.u) + prob * args.bound_stride;
+                lp = static_cast<const T*>(args.l) + prob * args.bound_stride;
+                upp = static_cast<const T*>(args.u) + prob * args.bound_stride;
 #pragma unroll
-                for (int i = 0; i < N; ++i) { x[i] = xp[i]; lo[i] = lp[i]; up[i] = upp[i]; }
+                for (int i = 0; i < N; ++i) x[i] = xp[i];
                 // validation, LS:930-943 (first failure wins)
                 bool finite = true, inb = true;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     finite = finite && (-Num<T>::inf() < x[i] && x[i] < Num<T>::inf());
-                    inb = inb && (lo[i] <= x[i]) && (x[i] <= up[i]);
+                    inb = inb && (lp[i] <= x[i]) && (x[i] <= upp[i]);
                 }
                 int vs = 0;
                 if (m == 0 || !finite) vs = mir_ls_badGuess;
@@ -117,11 +162,11 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                     ret.status = vs; ret.iterations = 0; ret.fCalls = 0; ret.gCalls = 0; ret.residual = Num<T>::inf(); ret.lambda = (T)0;
                     static_cast<Result*>(args.results)[prob] = ret;          // x is left untouched
                 } else {
-                    active = true; init = true;
+                    active = true; init = true; resume = false; specOK = false; pend = false; nterm = 0; specKind = JAC_NONE_;
                     tp = gridPerProblem ? tptr + prob * (unsigned long long)m : st_;
                     if (Model::kHasData) {
                         const T* yp = yptr + prob * (unsigned long long)m;
-#pragma unroll 4
+#pragma unroll 8
                         for (int row = 0; row < m; ++row) YO(row) = yp[row];
                     }
 #pragma unroll
@@ -129,22 +174,27 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                     maxAge = st.maxAge ? st.maxAge : (FD ? 2u * N : 3u);                             // LS:945
                     ysel = 0; iterations = 0; fCalls = 0; gCalls = 0; status = mir_ls_maxIterations;
                     residual = Num<T>::inf(); lambda = (T)0; mu = (T)1; deltaX_dot = (T)0;
+                    age = maxAge; needJacobian = false; fConverged = false;
                 }
             }
         }
         if (__all_sync(0xffffffffu, retired)) break;
 
-        // ------------------------------------------------------------------ guards of this pass, LS:974-995
-        int jacMode = JAC_NONE_;
-        bool doEval = false, skipRest = false, finished = false;
+        // ------------------------------------------------------------------ guards of this pass, LS:974-995, and the Jacobian decision, LS:996-1015
+        int rowMode = ROW_NONE_, rowKind = JAC_NONE_;
+        bool skipRest = false, finished = false, gtest = false, fdFresh = false;
         if (active) {
-            if (init) doEval = true;                       // initial residual, LS:953-956
-            else {
+            if (init) {
+                // initial residual, LS:953-956; the first Jacobian step is always a fresh one at x (age == maxAge)
+                rowMode = ROW_EVAL_; rowKind = FD ? JAC_NONE_ : JAC_FRESH_;
+            } else if (resume) {
+                resume = false; gtest = true;                   // Jacobian step of this pass done by the INSTALL row pass
+            } else {
                 ++sPasses;
                 if (fConverged) { status = mir_ls_fConverged; finished = true; }                         // LS:974-978
                 else if (!(lambda <= st.maxLambda)) { status = mir_ls_furtherImprovement; finished = true; }   // LS:979-983
                 else {
-                    if (mu > (T)16 && age) { needJacobian = true; age = maxAge; mu = (T)1; }             // LS:984-989
+                    if (mu > (T)16 && age) { needJacobian = true; age = maxAge; mu = (T)1; specOK = false; }   // LS:984-989
                     bool nan = false;                                                                    // LS:990-995
 #pragma unroll
                     for (int i = 0; i < N; ++i) nan = nan || !(x[i] <= x[i]);
@@ -159,22 +209,26 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                         status = mir_ls_furtherImprovement; finished = true;
                     } else if (needJacobian) {                                                           // LS:996-998
                         needJacobian = false;
-                        if (age < maxAge) { ++age; jacMode = JAC_BROYDEN_; ++sBroyden; }                 // LS:999-1007
-                        else { age = 0; jacMode = JAC_FRESH_; ++sFresh; if (FD) fCalls += N; else gCalls += 1; }   // LS:1010-1015, 1049
+                        int mode;
+                        if (age < maxAge) { ++age; mode = JAC_BROYDEN_; ++sBroyden; }                    // LS:999-1007
+                        else { age = 0; mode = JAC_FRESH_; ++sFresh; if (FD) fCalls += N; else gCalls += 1; }   // LS:1010-1015, 1049
+                        if (specOK && specKind == mode) gtest = true;            // built speculatively by the accepted trial's row pass
+                        else if (FD && mode == JAC_FRESH_) { fdFresh = true; gtest = true; }
+                        else { rowMode = ROW_INSTALL_; rowKind = mode; }
+                        specOK = false;
                     }
                 }
             }
         }
-        const bool go = active && !finished;
 
-        // ------------------------------------------------------------------ Jacobian phase + J^T y, J^T J
-        if (go && jacMode != JAC_NONE_) {
-            if (jacMode == JAC_FRESH_ && FD) {                                                           // LS:1018-1049
+        // ------------------------------------------------------------------ finite-difference fresh Jacobian, LS:1018-1049 (+ J^T y, J^T J)
+        if constexpr (FD) {
+            if (active && !finished && fdFresh) {
 #pragma unroll 1
                 for (int j = 0; j < N; ++j) {
                     T save = (T)0, lj = (T)0, uj = (T)0;
 #pragma unroll
-                    for (int i = 0; i < N; ++i) if (i == j) { save = x[i]; lj = lo[i]; uj = up[i]; }
+                    for (int i = 0; i < N; ++i) if (i == j) { save = x[i]; lj = lp[i]; uj = upp[i]; }
                     const T xmh = t_max(save - st.jacobianEpsilon, lj);
                     const T xph = t_min(save + st.jacobianEpsilon, uj);
                     const T twh = xph - xmh;
@@ -185,19 +239,22 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                         const typename Model::Pre prep = Model::prepare(pp);
                         const typename Model::Pre prem = Model::prepare(pm);
                         const T rt = rcp_ni(twh);
-                        int row = 0;
+                        constexpr int NE = Model::NE;
 #pragma unroll 1
-                        for (; row + 2 <= m; row += 2) {
+                        for (int row = 0; row < m; row += 2) {
+                            const bool two = row + 1 < m;
+                            const int rowB = two ? row + 1 : row;
                             const T t0 = Model::kHasData ? tp[row] : (T)0, y0 = Model::kHasData ? YO(row) : (T)0;
-                            const T t1 = Model::kHasData ? tp[row + 1] : (T)0, y1 = Model::kHasData ? YO(row + 1) : (T)0;
-                            const T fp0 = Model::residual(prep, pp, row, t0, y0), fm0 = Model::residual(prem, pm, row, t0, y0);
-                            const T fp1 = Model::residual(prep, pp, row + 1, t1, y1), fm1 = Model::residual(prem, pm, row + 1, t1, y1);
+                            const T t1 = Model::kHasData ? tp[rowB] : (T)0, y1 = Model::kHasData ? YO(rowB) : (T)0;
+                            T ea[4 * NE], ee[4 * NE];                     // the exps of f(x+h), f(x-h) for both rows, interleaved
+                            Model::exp_args(prep, pp, t0, ea); Model::exp_args(prem, pm, t0, ea + NE);
+                            Model::exp_args(prep, pp, t1, ea + 2 * NE); Model::exp_args(prem, pm, t1, ea + 3 * NE);
+                            exp_repro_many<4 * NE>(ea, ee);
+                            T fp0, fm0, fp1, fm1;
+                            Model::finish_r(prep, pp, t0, y0, ee, fp0); Model::finish_r(prem, pm, t0, y0, ee + NE, fm0);
+                            Model::finish_r(prep, pp, t1, y1, ee + 2 * NE, fp1); Model::finish_r(prem, pm, t1, y1, ee + 3 * NE, fm1);
                             JE(row, j) = (fp0 - fm0) * rt;                                               // LS:1040-1042
-                            JE(row + 1, j) = (fp1 - fm1) * rt;
-                        }
-                        for (; row < m; ++row) {
-                            const T tt = Model::kHasData ? tp[row] : (T)0, yo = Model::kHasData ? YO(row) : (T)0;
-                            JE(row, j) = (Model::residual(prep, pp, row, tt, yo) - Model::residual(prem, pm, row, tt, yo)) * rt;
+                            if (two) JE(rowB, j) = (fp1 - fm1) * rt;
                         }
                         sEvals += 2;
                     } else {
@@ -205,80 +262,46 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                         for (int row = 0; row < m; ++row) JE(row, j) = (T)0;                             // LS:1045-1047
                     }
                 }
-            }
-            T pJy[N], pJJ[NP];
+                pend = false;
+                T pJy[N], pJJ[NP];
 #pragma unroll
-            for (int i = 0; i < N; ++i) pJy[i] = (T)0;
+                for (int i = 0; i < N; ++i) pJy[i] = (T)0;
 #pragma unroll
-            for (int i = 0; i < NP; ++i) pJJ[i] = (T)0;
-            const typename Model::Pre pre = Model::prepare(x);
-            const T negd = (jacMode == JAC_BROYDEN_) ? -rcp_ni(deltaX_dot) : (T)0;                       // LS:1001
-            const T* const yv = ysel ? pB1 : pB0;            // y  = f at the current point
-            const T* const fo = ysel ? pB0 : pB1;            // mBuffer = f at the previous point (Broyden)
-            auto jrow = [&](int row, T yr, T fold, T tt, T (&Jr)[N]) {
-                if (jacMode == JAC_FRESH_ && !FD) {                                                      // LS:1011-1015
-                    Model::jacobian(pre, x, row, tt, Jr);
+                for (int i = 0; i < NP; ++i) pJJ[i] = (T)0;
+                const T* const yv = ysel ? pB1 : pB0;
+#pragma unroll 2
+                for (int row = 0; row < m; ++row) {                                                      // LS:1052, 1065
+                    const T yr = yv[row * NT];
+                    T Jr[N];
 #pragma unroll
-                    for (int i = 0; i < N; ++i) JE(row, i) = Jr[i];
-                } else if (jacMode == JAC_BROYDEN_) {                                                    // LS:1003-1006
-                    T acc = (T)0;
+                    for (int i = 0; i < N; ++i) Jr[i] = JE(row, i);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) acc += Jr[i] * dX[i];
-                    const T v = ((fold - yr) + acc) * negd;
+                    for (int i = 0; i < N; ++i) {
+                        pJy[i] += Jr[i] * yr;
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { Jr[i] += v * dX[i]; JE(row, i) = Jr[i]; }
+                        for (int j = 0; j <= i; ++j) pJJ[tri(i, j)] += Jr[i] * Jr[j];
+                    }
                 }
-            };
-            auto accum = [&](T yr, const T (&Jr)[N]) {                                                   // LS:1052, 1065
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    pJy[i] += Jr[i] * yr;
+                for (int i = 0; i < N; ++i) Jy[i] = pJy[i];
 #pragma unroll
-                    for (int j = 0; j <= i; ++j) pJJ[tri(i, j)] += Jr[i] * Jr[j];
-                }
-            };
-            const bool loadJ = !(jacMode == JAC_FRESH_ && !FD);
-            const bool isBro = jacMode == JAC_BROYDEN_;
-            int row = 0;
-#pragma unroll 1
-            for (; row + 2 <= m; row += 2) {
-                T Ja[N], Jb[N];
-                const T ya = yv[row * NT], yb = yv[(row + 1) * NT];
-                const T fa = isBro ? fo[row * NT] : (T)0, fb = isBro ? fo[(row + 1) * NT] : (T)0;
-                const T ta = (Model::kHasData && !loadJ) ? tp[row] : (T)0, tb = (Model::kHasData && !loadJ) ? tp[row + 1] : (T)0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) { Ja[i] = loadJ ? JE(row, i) : (T)0; Jb[i] = loadJ ? JE(row + 1, i) : (T)0; }
-                jrow(row, ya, fa, ta, Ja);
-                jrow(row + 1, yb, fb, tb, Jb);
-                accum(ya, Ja);
-                accum(yb, Jb);
+                for (int i = 0; i < NP; ++i) JJ[i] = pJJ[i];
             }
-            for (; row < m; ++row) {
-                T Ja[N];
-                const T ya = yv[row * NT];
-                const T fa = isBro ? fo[row * NT] : (T)0;
-                const T ta = (Model::kHasData && !loadJ) ? tp[row] : (T)0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) Ja[i] = loadJ ? JE(row, i) : (T)0;
-                jrow(row, ya, fa, ta, Ja);
-                accum(ya, Ja);
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) Jy[i] = pJy[i];
-#pragma unroll
-            for (int i = 0; i < NP; ++i) JJ[i] = pJJ[i];
+        }
 
-            T gsel = Jy[0]; T gbest = t_abs(Jy[0]);                                                      // LS:1053 (iamax: first max |.|)
+        // ------------------------------------------------------------------ gradient test, LS:1053-1062
+        if (active && !finished && gtest) {
+            T gsel = Jy[0]; T gbest = t_abs(Jy[0]);                                                      // iamax: first max |.|
 #pragma unroll
             for (int i = 1; i < N; ++i) { const T v = t_abs(Jy[i]); if (v > gbest) { gbest = v; gsel = Jy[i]; } }
-            if (!(t_abs(gsel) > st.gradTolerance)) {                                                     // LS:1053-1062
+            if (!(t_abs(gsel) > st.gradTolerance)) {
                 if (age == 0) { status = mir_ls_gConverged; finished = true; }
                 else { age = maxAge; skipRest = true; }
             }
         }
 
         // ------------------------------------------------------------------ step: lambda init, BOXCQP, trial point
-        if (active && !finished && !init && !skipRest) {
+        if (active && !finished && !init && !skipRest && rowMode != ROW_INSTALL_) {
             if (!(lambda >= st.minLambda)) {                                                             // LS:1067-1072
                 T dmax = JJ[0];
 #pragma unroll
@@ -286,9 +309,9 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                 lambda = (T)(0.001 * (double)dmax);
                 if (!(lambda >= st.minLambda)) lambda = (T)1;
             }
-            T qpl[N], qpu[N];                                                                            // LS:1074-1077
+            T qpl[N], qpu[N], lo[N], up[N];                                                              // LS:1074-1077
 #pragma unroll
-            for (int i = 0; i < N; ++i) { qpl[i] = lo[i] - x[i]; qpu[i] = up[i] - x[i]; }
+            for (int i = 0; i < N; ++i) { lo[i] = lp[i]; up[i] = upp[i]; qpl[i] = lo[i] - x[i]; qpu[i] = up[i] - x[i]; }
             QPCounters qc{0, 0};
             const int qps = boxqp_small<T, N>(st.qpSettings, JJ, lambda, Jy, qpl, qpu, dX, qc);          // LS:1078-1080
             sSolves += qc.solves; sQPIt += qc.iterations;
@@ -309,52 +332,235 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                         same = same && (xt[i] == x[i]) && (signbit(xt[i]) == signbit(x[i]));
                     }
                     ++fCalls;                                                                            // LS:1112
-                    doEval = !same;        // f(xt) == y bit for bit when xt == x: evaluation skipped, trial = residual
+                    // f(xt) == y bit for bit when xt == x: evaluation skipped, trial = residual (a rejection)
+                    if (!same) {
+                        rowMode = ROW_EVAL_;
+                        // what the next pass's Jacobian step will be if this trial is accepted (mu = 1 after an accept,
+                        // so LS:984-989 cannot intervene; LS:1171 can still force a fresh one: checked at the guards)
+                        rowKind = (age < maxAge) ? JAC_BROYDEN_ : (FD ? JAC_NONE_ : JAC_FRESH_);
+                    }
                 }
             }
         }
 
-        // ------------------------------------------------------------------ trial evaluation, LS:1113-1115 (and LS:953-955)
+        // ------------------------------------------------------------------ row phase: f (LS:953, 1113) + Jacobian step of the next pass (LS:999-1015, 1052, 1065)
         T trial = residual;
-        if (active && !finished && doEval) {
+        T pJy[N], pJJ[NP];
+        if (active && !finished && rowMode != ROW_NONE_) {
+            const bool isEval = rowMode == ROW_EVAL_;
+            const bool kB = rowKind == JAC_BROYDEN_, kF = rowKind == JAC_FRESH_;
+            const bool pnd = kB && pend;
+            if (!isEval) {                                      // INSTALL evaluates at x (xt is scratch until the next QP)
+#pragma unroll
+                for (int i = 0; i < N; ++i) xt[i] = x[i];
+            }
             const typename Model::Pre pre = Model::prepare(xt);
-            T acc = (T)0;
-            T* const out = ysel ? pB0 : pB1;                   // mBuffer = the buffer that is not y
-            constexpr int U = 4;                               // independent rows in flight: their exp chains interleave
-            int row = 0;
+            // EVAL: f goes to mBuffer (the buffer that is not y), the previous point's residuals are y.
+            // INSTALL: f(x) is recomputed (== y, not stored), the previous point's residuals are mBuffer.
+            T* const out = ysel ? pB0 : pB1;
+            const T* const fold = isEval ? (ysel ? pB1 : pB0) : (ysel ? pB0 : pB1);
+            const T negd = kB ? -rcp_ni(isEval ? nd : deltaX_dot) : (T)0;                                // LS:1001
+#pragma unroll
+            for (int i = 0; i < N; ++i) pJy[i] = (T)0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) pJJ[i] = (T)0;
+            T acc2 = (T)0;
+
+            constexpr int NE = Model::NE;
+            if constexpr (VL) {
+                const int k = nterm;                             // terms already in the list; this pass computes term k
+                T* const pVk = pV + (size_t)k * m * NT;
+                T anchor[N], d0[N], d1[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    anchor[i] = kB ? dXp[i] : xt[i];
+                    d0[i] = (kB && k > 0) ? DL(0, i) : (T)0;
+                    d1[i] = (kB && k > 1) ? DL(1, i) : (T)0;
+                }
+                const typename Model::Pre preA = Model::prepare(anchor);
+                struct RowIn { T tt, yo, fo, v0, v1; };
+                auto rowLoad = [&](int row, RowIn& in, bool on) {
+                    in.tt = (Model::kHasData && on) ? tp[row] : (T)0;
+                    in.yo = (Model::kHasData && on) ? YO(row) : (T)0;
+                    in.fo = (kB && on) ? fold[row * NT] : (T)0;
+                    in.v0 = (kB && k > 0 && on) ? pV[row * NT] : (T)0;
+                    in.v1 = (kB && k > 1 && on) ? pV[(size_t)m * NT + row * NT] : (T)0;
+                };
+                // Branch-free: every lane runs the Broyden arithmetic (selects pick the result, loads and stores are
+                // predicated).  eT / eA: the exps of this row at the trial point and at the anchor.
+                auto rowFinish = [&](int row, const RowIn& in, const T* eT, const T* eA, bool on) {
+                    T r, Jf[N], Jr[N], Jn[N];
+                    Model::finish_rj(pre, xt, in.tt, in.yo, eT, r, Jf);               // f and the fresh-Jacobian candidate
+                    Model::finish_j(preA, anchor, in.tt, eA, Jr);                     // g_row(x_anchor), then the accepted terms
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const T j1 = fma(in.v0, d0[i], Jr[i]);
+                        Jr[i] = (k > 0) ? j1 : Jr[i];
+                        const T j2 = fma(in.v1, d1[i], Jr[i]);
+                        Jr[i] = (k > 1) ? j2 : Jr[i];
+                    }
+                    T acc = (T)0;                                                     // LS:1002-1006
+#pragma unroll
+                    for (int i = 0; i < N; ++i) acc = fma(Jr[i], dX[i], acc);
+                    const T v = ((in.fo - r) + acc) * negd;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) Jn[i] = kB ? fma(v, dX[i], Jr[i]) : Jf[i];
+                    if (kB && on) pVk[row * NT] = v;
+                    if (isEval && on) out[row * NT] = r;
+                    if (on) {
+                        acc2 = fma(r, r, acc2);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {                                 // LS:1052, 1065
+                            pJy[i] = fma(Jn[i], r, pJy[i]);
+#pragma unroll
+                            for (int j = 0; j <= i; ++j) pJJ[tri(i, j)] = fma(Jn[i], Jn[j], pJJ[tri(i, j)]);
+                        }
+                    }
+                };
+                // A pair of rows: four independent exp batches (2 rows x {trial point, anchor}) in one interleaved call.
+                auto pairCompute = [&](int row, const RowIn& A, const RowIn& B, bool two) {
+                    T ea[4 * NE], ee[4 * NE];
+                    Model::exp_args(pre, xt, A.tt, ea); Model::exp_args(pre, xt, B.tt, ea + NE);
+                    Model::exp_args(preA, anchor, A.tt, ea + 2 * NE); Model::exp_args(preA, anchor, B.tt, ea + 3 * NE);
+                    exp_repro_many<4 * NE>(ea, ee);
+                    rowFinish(row, A, ee, ee + 2 * NE, true);
+                    rowFinish(row + 1, B, ee + NE, ee + 3 * NE, two);
+                };
+                int row = 0;
+                RowIn ra, rb;
+                rowLoad(0, ra, m >= 2); rowLoad(1, rb, m >= 2);
 #pragma unroll 1
-            for (; row + U <= m; row += U) {
-                T tt[U], yo[U], r[U];
+                for (; row + 2 <= m; row += 2) {
+                    RowIn na, nb;
+                    const bool more = row + 4 <= m;
+                    rowLoad(row + 2, na, more); rowLoad(row + 3, nb, more);
+                    pairCompute(row, ra, rb, true);
+                    ra = na; rb = nb;
+                }
+                if (row < m) { rowLoad(row, ra, true); pairCompute(row, ra, ra, false); }
+            } else {
+                // Stored-J scheme.  One row = slab/shared loads (issued a pair of rows ahead: their latency hides behind
+                // the previous pair's exp chains) + compute.
+                struct RowIn { T tt, yo, fo, vp; T Jr[N]; };
+                auto rowLoad = [&](int row, RowIn& in, bool on) {
+                    in.tt = (Model::kHasData && on) ? tp[row] : (T)0;
+                    in.yo = (Model::kHasData && on) ? YO(row) : (T)0;
 #pragma unroll
-                for (int u = 0; u < U; ++u) { tt[u] = Model::kHasData ? tp[row + u] : (T)0; yo[u] = Model::kHasData ? YO(row + u) : (T)0; }
+                    for (int i = 0; i < N; ++i) in.Jr[i] = (kB && on) ? JE(row, i) : (T)0;
+                    in.fo = (kB && on) ? fold[row * NT] : (T)0;
+                    in.vp = (pnd && on) ? pV[row * NT] : (T)0;
+                };
+                auto rowFinish = [&](int row, RowIn& in, const T* eT, bool on) {
+                    T r, Jn[N];
+                    if constexpr (!FD) Model::finish_rj(pre, xt, in.tt, in.yo, eT, r, Jn);   // f and the fresh-Jacobian candidate
+                    else {
+                        Model::finish_r(pre, xt, in.tt, in.yo, eT, r);
 #pragma unroll
-                for (int u = 0; u < U; ++u) r[u] = Model::residual(pre, xt, row + u, tt[u], yo[u]);
+                        for (int i = 0; i < N; ++i) Jn[i] = (T)0;
+                    }
+                    if (kB && on) {
+                        if (pnd) {                                                  // materialise the pending rank-1 term
 #pragma unroll
-                for (int u = 0; u < U; ++u) { out[(row + u) * NT] = r[u]; acc += r[u] * r[u]; }
+                            for (int i = 0; i < N; ++i) in.Jr[i] = fma(in.vp, dXp[i], in.Jr[i]);
+                            if (isEval) {
+#pragma unroll
+                                for (int i = 0; i < N; ++i) JE(row, i) = in.Jr[i];
+                            }
+                        }
+                        T acc = (T)0;                                               // LS:1002-1006
+#pragma unroll
+                        for (int i = 0; i < N; ++i) acc = fma(in.Jr[i], dX[i], acc);
+                        const T v = ((in.fo - r) + acc) * negd;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) Jn[i] = fma(v, dX[i], in.Jr[i]);
+                        if (isEval) pV[row * NT] = v;
+                    }
+                    if (on && (kF || (kB && !isEval))) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) JE(row, i) = Jn[i];
+                    }
+                    if (isEval && on) out[row * NT] = r;
+                    if (on) {
+                        acc2 = fma(r, r, acc2);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {                               // LS:1052, 1065
+                            pJy[i] = fma(Jn[i], r, pJy[i]);
+#pragma unroll
+                            for (int j = 0; j <= i; ++j) pJJ[tri(i, j)] = fma(Jn[i], Jn[j], pJJ[tri(i, j)]);
+                        }
+                    }
+                };
+                auto pairCompute = [&](int row, RowIn& A, RowIn& B, bool two) {
+                    T ea[2 * NE], ee[2 * NE];
+                    Model::exp_args(pre, xt, A.tt, ea); Model::exp_args(pre, xt, B.tt, ea + NE);
+                    exp_repro_many<2 * NE>(ea, ee);
+                    rowFinish(row, A, ee, true);
+                    rowFinish(row + 1, B, ee + NE, two);
+                };
+                int row = 0;
+                RowIn ra, rb;
+                rowLoad(0, ra, m >= 2); rowLoad(1, rb, m >= 2);
+#pragma unroll 1
+                for (; row + 2 <= m; row += 2) {
+                    RowIn na, nb;
+                    const bool more = row + 4 <= m;
+                    rowLoad(row + 2, na, more); rowLoad(row + 3, nb, more);
+                    pairCompute(row, ra, rb, true);
+                    ra = na; rb = nb;
+                }
+                if (row < m) { rowLoad(row, ra, true); rb = ra; pairCompute(row, ra, rb, false); }
             }
-            for (; row < m; ++row) {
-                const T r = Model::residual(pre, xt, row, Model::kHasData ? tp[row] : (T)0, Model::kHasData ? YO(row) : (T)0);
-                out[row * NT] = r;
-                acc += r * r;
-            }
-            trial = acc;
-            ++sEvals;
+            if (isEval) { trial = acc2; ++sEvals; }
         }
 
         // ------------------------------------------------------------------ accept / reject, LS:1117-1175
         if (active && !finished) {
             const bool wasInit = init;
-            if (init) {                                                                                  // LS:953-971
+            bool passEnds = true;
+            if (rowMode == ROW_INSTALL_) {
+                // the Jacobian step of this pass (LS:996-1052, 1065) is done; g-test and QP follow in the next warp pass
+#pragma unroll
+                for (int i = 0; i < N; ++i) Jy[i] = pJy[i];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) JJ[i] = pJJ[i];
+                if constexpr (VL) {
+                    if (rowKind == JAC_BROYDEN_) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) DL(nterm, i) = dX[i];
+                        ++nterm;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) dXp[i] = x[i];
+                        nterm = 0;
+                    }
+                }
+                pend = false; resume = true; passEnds = false;
+            } else if (init) {                                                                           // LS:953-971
                 init = false;
                 residual = trial; ysel ^= 1; fCalls = 1;
                 fConverged = residual <= st.maxGoodResidual;
                 needJacobian = true; age = maxAge;
+                if (rowKind == JAC_FRESH_) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) Jy[i] = pJy[i];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) JJ[i] = pJJ[i];
+                    specOK = true; specKind = JAC_FRESH_; pend = false;
+                    if constexpr (VL) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) dXp[i] = x[i];
+                        nterm = 0;
+                    }
+                }
             } else if (!skipRest) {
                 if (!(trial <= Num<T>::inf())) { status = mir_ls_numericError; finished = true; }        // LS:1117-1122
                 else {
                     const T improvement = residual - trial;                                              // LS:1124
-                    if (!(improvement > (T)0)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; }         // LS:1125-1130
-                    else {
+                    if (!(improvement > (T)0)) {                                                         // LS:1125-1130
+                        lambda *= st.lambdaIncrease * mu; mu *= (T)2;
+                        // rejected: a materialised pending term stays materialised, a speculative fresh J overwrote a dead J
+                        if (rowMode == ROW_EVAL_ && rowKind != JAC_NONE_) pend = false;
+                    } else {
                         needJacobian = true; mu = (T)1; ++iterations; ++sAccepted;                       // LS:1132-1139
 #pragma unroll
                         for (int i = 0; i < N; ++i) x[i] = xt[i];
@@ -372,6 +578,29 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                             pred += Jy[i] * dX[i];
                         }
                         pred = -pred;
+                        // the speculative Jacobian step becomes the state (used only if the run continues)
+                        if (rowKind != JAC_NONE_) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) Jy[i] = pJy[i];
+#pragma unroll
+                            for (int i = 0; i < NP; ++i) JJ[i] = pJJ[i];
+                            specOK = true; specKind = rowKind;
+                            if constexpr (VL) {
+                                if (rowKind == JAC_BROYDEN_) {
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) DL(nterm, i) = dX[i];
+                                    ++nterm;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) dXp[i] = x[i];
+                                    nterm = 0;
+                                }
+                            } else {
+                                pend = rowKind == JAC_BROYDEN_;
+#pragma unroll
+                                for (int i = 0; i < N; ++i) dXp[i] = dX[i];
+                            }
+                        }
                         if (!(pred > (T)0)) { status = mir_ls_furtherImprovement; finished = true; }     // LS:1144-1148
                         else {
                             const T rho = div_ni(pred, improvement);                                     // LS:1150
@@ -398,7 +627,7 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                 }
             }
             // LS:1175 (a do-while: the first pass always runs)
-            if (!wasInit && !finished && !(iterations < st.maxIterations)) { status = mir_ls_maxIterations; finished = true; }
+            if (passEnds && !wasInit && !finished && !(iterations < st.maxIterations)) { status = mir_ls_maxIterations; finished = true; }
         }
 
         if (active && finished) {
@@ -414,22 +643,23 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
     }
 
     if (args.stats) {
-        auto wsum = [](unsigned long long v) {
+        auto wsum = [](unsigned v32) {
+            unsigned long long v = v32;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             return v;
         };
-        sProblems = wsum(sProblems); sPasses = wsum(sPasses); sAccepted = wsum(sAccepted); sFresh = wsum(sFresh);
-        sBroyden = wsum(sBroyden); sEvals = wsum(sEvals); sSolves = wsum(sSolves); sQPIt = wsum(sQPIt);
-        if ((tid & 31) == 0 && sProblems) {
-            atomicAdd((unsigned long long*)&args.stats->problems, sProblems);
-            atomicAdd((unsigned long long*)&args.stats->passes, sPasses);
-            atomicAdd((unsigned long long*)&args.stats->accepted, sAccepted);
-            atomicAdd((unsigned long long*)&args.stats->fresh_jacobians, sFresh);
-            atomicAdd((unsigned long long*)&args.stats->broyden_updates, sBroyden);
-            atomicAdd((unsigned long long*)&args.stats->model_evals, sEvals);
-            atomicAdd((unsigned long long*)&args.stats->qp_solves, sSolves);
-            atomicAdd((unsigned long long*)&args.stats->qp_iterations, sQPIt);
+        const unsigned long long wProblems = wsum(sProblems), wPasses = wsum(sPasses), wAccepted = wsum(sAccepted), wFresh = wsum(sFresh);
+        const unsigned long long wBroyden = wsum(sBroyden), wEvals = wsum(sEvals), wSolves = wsum(sSolves), wQPIt = wsum(sQPIt);
+        if ((tid & 31) == 0 && wProblems) {
+            atomicAdd((unsigned long long*)&args.stats->problems, wProblems);
+            atomicAdd((unsigned long long*)&args.stats->passes, wPasses);
+            atomicAdd((unsigned long long*)&args.stats->accepted, wAccepted);
+            atomicAdd((unsigned long long*)&args.stats->fresh_jacobians, wFresh);
+            atomicAdd((unsigned long long*)&args.stats->broyden_updates, wBroyden);
+            atomicAdd((unsigned long long*)&args.stats->model_evals, wEvals);
+            atomicAdd((unsigned long long*)&args.stats->qp_solves, wSolves);
+            atomicAdd((unsigned long long*)&args.stats->qp_iterations, wQPIt);
         }
     }
 }

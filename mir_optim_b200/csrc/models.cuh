@@ -30,6 +30,9 @@ template <class T> struct ModelLinear2 {
     __device__ static void jacobian(const Pre&, const T (&)[N], int row, T, T (&J)[N]) {
         J[0] = row == 0 ? (T)1 : (T)0; J[1] = row == 0 ? (T)0 : (T)-1;
     }
+    __device__ static void residual_jacobian(const Pre& q, const T (&p)[N], int row, T t, T y, T& r, T (&J)[N]) {
+        r = residual(q, p, row, t, y); jacobian(q, p, row, t, J);
+    }
 };
 
 // Rosenbrock: r = (10 (p1 - p0^2), 1 - p0)                     least_squares.d:261-265, 295-301
@@ -42,6 +45,9 @@ template <class T> struct ModelRosenbrock {
     }
     __device__ static void jacobian(const Pre&, const T (&p)[N], int row, T, T (&J)[N]) {
         J[0] = row == 0 ? mul_rn((T)-20, p[0]) : (T)-1; J[1] = row == 0 ? (T)10 : (T)0;
+    }
+    __device__ static void residual_jacobian(const Pre& q, const T (&p)[N], int row, T t, T y, T& r, T (&J)[N]) {
+        r = residual(q, p, row, t, y); jacobian(q, p, row, t, J);
     }
 };
 
@@ -57,87 +63,120 @@ template <class T> struct ModelSqrtCircle {
         const T s = sqrt_ni(sub_rn((T)1, add_rn(mul_rn(p[0], p[0]), mul_rn(p[1], p[1]))));
         J[0] = div_ni(-p[0], s); J[1] = div_ni(-p[1], s);
     }
+    __device__ static void residual_jacobian(const Pre& q, const T (&p)[N], int row, T t, T y, T& r, T (&J)[N]) {
+        r = residual(q, p, row, t, y); jacobian(q, p, row, t, J);
+    }
+};
+
+// The exponential models are written in three pieces so that a caller can batch the exps of several rows / points
+// into one interleaved exp_repro_many call:  exp_args (the NE exp arguments of a row), then finish_r / finish_j /
+// finish_rj (residual and/or Jacobian row from the NE exp values).  residual(), jacobian() and residual_jacobian()
+// are defined through the same pieces, so every path performs the same operations in the same order.
+template <class M, class T, bool INL> struct ExpModelBase {
+    template <class P, int NN> __device__ static T residual(const P& q, const T (&p)[NN], int, T t, T y) {
+        T a[M::NE], e[M::NE], r;
+        M::exp_args(q, p, t, a);
+#pragma unroll
+        for (int k = 0; k < M::NE; ++k) e[k] = exp_sel<INL>(a[k]);
+        M::finish_r(q, p, t, y, e, r);
+        return r;
+    }
+    template <class P, int NN> __device__ static void jacobian(const P& q, const T (&p)[NN], int, T t, T (&J)[NN]) {
+        T a[M::NE], e[M::NE];
+        M::exp_args(q, p, t, a);
+#pragma unroll
+        for (int k = 0; k < M::NE; ++k) e[k] = exp_sel<INL>(a[k]);
+        M::finish_j(q, p, t, e, J);
+    }
+    template <class P, int NN> __device__ static void residual_jacobian(const P& q, const T (&p)[NN], int, T t, T y, T& r, T (&J)[NN]) {
+        T a[M::NE], e[M::NE];
+        M::exp_args(q, p, t, a);
+#pragma unroll
+        for (int k = 0; k < M::NE; ++k) e[k] = exp_sel<INL>(a[k]);
+        M::finish_r(q, p, t, y, e, r);
+        M::finish_j(q, p, t, e, J);
+    }
+    template <class P, int NN> __device__ static void finish_rj(const P& q, const T (&p)[NN], T t, T y, const T* e, T& r, T (&J)[NN]) {
+        M::finish_r(q, p, t, y, e, r);
+        M::finish_j(q, p, t, e, J);
+    }
 };
 
 // r_i = p0 exp(-t_i p1) - y_i                                  least_squares.d:347, 360
-template <class T, bool INL = false> struct ModelExpDecay2 {
-    static constexpr int N = 2; static constexpr bool kHasData = true;
+template <class T, bool INL = false> struct ModelExpDecay2 : ExpModelBase<ModelExpDecay2<T, INL>, T, INL> {
+    static constexpr int N = 2, NE = 1; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
-        return sub_rn(mul_rn(p[0], exp_sel<INL>(mul_rn(-t, p[1]))), y);
-    }
-    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        const T e = exp_sel<INL>(mul_rn(-t, p[1]));
-        J[0] = e; J[1] = mul_rn(-mul_rn(p[0], t), e);
+    __device__ static void exp_args(const Pre&, const T (&p)[N], T t, T* a) { a[0] = mul_rn(-t, p[1]); }
+    __device__ static void finish_r(const Pre&, const T (&p)[N], T, T y, const T* e, T& r) { r = sub_rn(mul_rn(p[0], e[0]), y); }
+    __device__ static void finish_j(const Pre&, const T (&p)[N], T t, const T* e, T (&J)[N]) {
+        J[0] = e[0]; J[1] = mul_rn(-mul_rn(p[0], t), e[0]);
     }
 };
 
 // r_i = p0 exp(-t_i / p1) + p2 - y_i                           least_squares.d:378, 390
-template <class T, bool INL = false> struct ModelExpTau3 {
-    static constexpr int N = 3; static constexpr bool kHasData = true;
+template <class T, bool INL = false> struct ModelExpTau3 : ExpModelBase<ModelExpTau3<T, INL>, T, INL> {
+    static constexpr int N = 3, NE = 1; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
-        return sub_rn(add_rn(mul_rn(p[0], exp_sel<INL>(div_ni(-t, p[1]))), p[2]), y);
-    }
-    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        const T e = exp_sel<INL>(div_ni(-t, p[1]));
-        J[0] = e; J[1] = div_ni(mul_rn(mul_rn(p[0], e), t), mul_rn(p[1], p[1])); J[2] = (T)1;
+    __device__ static void exp_args(const Pre&, const T (&p)[N], T t, T* a) { a[0] = div_ni(-t, p[1]); }
+    __device__ static void finish_r(const Pre&, const T (&p)[N], T, T y, const T* e, T& r) { r = sub_rn(add_rn(mul_rn(p[0], e[0]), p[2]), y); }
+    __device__ static void finish_j(const Pre&, const T (&p)[N], T t, const T* e, T (&J)[N]) {
+        J[0] = e[0]; J[1] = div_ni(mul_rn(mul_rn(p[0], e[0]), t), mul_rn(p[1], p[1])); J[2] = (T)1;
     }
 };
 
 // r_i = p0 exp(-p1 t_i) + p2 - y_i                             BASELINE configs[0]
-template <class T, bool INL = false> struct ModelExpDecay3 {
-    static constexpr int N = 3; static constexpr bool kHasData = true;
+template <class T, bool INL = false> struct ModelExpDecay3 : ExpModelBase<ModelExpDecay3<T, INL>, T, INL> {
+    static constexpr int N = 3, NE = 1; static constexpr bool kHasData = true;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
-        return sub_rn(add_rn(mul_rn(p[0], exp_sel<INL>(mul_rn(-p[1], t))), p[2]), y);
-    }
-    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
-        const T e = exp_sel<INL>(mul_rn(-p[1], t));
-        J[0] = e; J[1] = mul_rn(-mul_rn(p[0], t), e); J[2] = (T)1;
+    __device__ static void exp_args(const Pre&, const T (&p)[N], T t, T* a) { a[0] = mul_rn(-p[1], t); }
+    __device__ static void finish_r(const Pre&, const T (&p)[N], T, T y, const T* e, T& r) { r = sub_rn(add_rn(mul_rn(p[0], e[0]), p[2]), y); }
+    __device__ static void finish_j(const Pre&, const T (&p)[N], T t, const T* e, T (&J)[N]) {
+        J[0] = e[0]; J[1] = mul_rn(-mul_rn(p[0], t), e[0]); J[2] = (T)1;
     }
 };
 
 // Gaussian peak on a baseline: r_i = A exp(-(t_i - mu)^2 / (2 sigma^2)) + c - y_i, p = (A, mu, sigma, c)
 //                                                             BASELINE configs[1]
-template <class T, bool INL = false> struct ModelGauss4 {
-    static constexpr int N = 4; static constexpr bool kHasData = true;
-    struct Pre { T is; };
+template <class T> struct Gauss4Pre { T is; };
+template <class T, bool INL = false> struct ModelGauss4 : ExpModelBase<ModelGauss4<T, INL>, T, INL> {
+    static constexpr int N = 4, NE = 1; static constexpr bool kHasData = true;
+    using Pre = Gauss4Pre<T>;
     __device__ static Pre prepare(const T (&p)[N]) { return {rcp_ni(p[2])}; }
-    __device__ static T residual(const Pre& q, const T (&p)[N], int, T t, T y) {
+    __device__ static void exp_args(const Pre& q, const T (&p)[N], T t, T* a) {
         const T z = mul_rn(sub_rn(t, p[1]), q.is);
-        return sub_rn(add_rn(mul_rn(p[0], exp_sel<INL>(mul_rn((T)-0.5, mul_rn(z, z)))), p[3]), y);
+        a[0] = mul_rn((T)-0.5, mul_rn(z, z));
     }
-    __device__ static void jacobian(const Pre& q, const T (&p)[N], int, T t, T (&J)[N]) {
+    __device__ static void finish_r(const Pre&, const T (&p)[N], T, T y, const T* e, T& r) { r = sub_rn(add_rn(mul_rn(p[0], e[0]), p[3]), y); }
+    __device__ static void finish_j(const Pre& q, const T (&p)[N], T t, const T* e, T (&J)[N]) {
         const T z = mul_rn(sub_rn(t, p[1]), q.is);
         const T zz = mul_rn(z, z);
-        const T e = exp_sel<INL>(mul_rn((T)-0.5, zz));
-        const T ae = mul_rn(p[0], e);
-        J[0] = e; J[1] = mul_rn(mul_rn(ae, z), q.is); J[2] = mul_rn(mul_rn(ae, zz), q.is); J[3] = (T)1;
+        const T ae = mul_rn(p[0], e[0]);
+        J[0] = e[0]; J[1] = mul_rn(mul_rn(ae, z), q.is); J[2] = mul_rn(mul_rn(ae, zz), q.is); J[3] = (T)1;
     }
 };
 
 // Sum of exponentials: r_i = sum_k p[2k] exp(-p[2k+1] t_i) - y_i          BASELINE configs[2]
-template <class T, int N_, bool INL = false> struct ModelSumExp {
-    static constexpr int N = N_; static constexpr bool kHasData = true;
+template <class T, int N_, bool INL = false> struct ModelSumExp : ExpModelBase<ModelSumExp<T, N_, INL>, T, INL> {
+    static constexpr int N = N_, NE = N_ / 2; static constexpr bool kHasData = true;
     static_assert(N_ % 2 == 0, "sum-of-exponentials has (amplitude, rate) pairs");
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
-    __device__ static T residual(const Pre&, const T (&p)[N], int, T t, T y) {
+    __device__ static void exp_args(const Pre&, const T (&p)[N], T t, T* a) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) a[k / 2] = mul_rn(-p[k + 1], t);
+    }
+    __device__ static void finish_r(const Pre&, const T (&p)[N], T, T y, const T* e, T& r) {
         T acc = (T)0;
 #pragma unroll
-        for (int k = 0; k < N; k += 2) acc = add_rn(acc, mul_rn(p[k], exp_sel<INL>(mul_rn(-p[k + 1], t))));
-        return sub_rn(acc, y);
+        for (int k = 0; k < N; k += 2) acc = add_rn(acc, mul_rn(p[k], e[k / 2]));
+        r = sub_rn(acc, y);
     }
-    __device__ static void jacobian(const Pre&, const T (&p)[N], int, T t, T (&J)[N]) {
+    __device__ static void finish_j(const Pre&, const T (&p)[N], T t, const T* e, T (&J)[N]) {
 #pragma unroll
-        for (int k = 0; k < N; k += 2) {
-            const T e = exp_sel<INL>(mul_rn(-p[k + 1], t));
-            J[k] = e; J[k + 1] = mul_rn(-mul_rn(p[k], t), e);
-        }
+        for (int k = 0; k < N; k += 2) { J[k] = e[k / 2]; J[k + 1] = mul_rn(-mul_rn(p[k], t), e[k / 2]); }
     }
 };
 

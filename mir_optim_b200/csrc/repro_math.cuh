@@ -21,51 +21,88 @@ namespace mirb200 {
 
 // (static: one private copy per translation unit, so the host-side stubs never collide at link time)
 
-static __device__ __forceinline__ double exp_repro_inl(double x)
+// Polynomial / reduction constants live in __constant__ memory: a DFMA takes a constant-bank operand directly,
+// while a 64-bit immediate costs two extra moves per use (ncu, round 1: 38 % of the thread-per-problem row loop
+// was constant materialisation).  Same bits as the literals they replace.
+static __constant__ double kExpD[17] = {
+    0x1.71547652b82fep+0, 0x1.62e42feep-1, 0x1.a39ef35793c76p-33,                     // log2(e), ln2 hi, ln2 lo
+    0x1.6124613a86d09p-33, 0x1.1eed8eff8d898p-29, 0x1.ae64567f544e4p-26, 0x1.27e4fb7789f5cp-22, 0x1.71de3a556c734p-19,
+    0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10, 0x1.1111111111111p-7, 0x1.5555555555555p-5,
+    0x1.5555555555555p-3, 0.5, 1.0, 1.0};
+static __constant__ float kExpS[11] = {
+    0x1.715476p+0f, 0x1.62e4p-1f, 0x1.7f7d1cp-20f,
+    0x1.a01a02p-13f, 0x1.6c16c2p-10f, 0x1.111112p-7f, 0x1.555556p-5f, 0x1.555556p-3f, 0.5f, 1.0f, 1.0f};
+
+// Branch-free on purpose: the range checks are selects at the end and the scaling is two exact power-of-two
+// multiplications (p * 2^(k/2) is exact, the second product rounds once -- the value ldexp returns, also into the
+// subnormals and into overflow).  exp_repro_many evaluates K independent arguments with the Horner steps
+// INTERLEAVED in source order, so the K dependent-FMA chains overlap in the pipe (ncu, round 1: with early returns
+// every exp was its own branch region, and even in one basic block ptxas emitted the chains one after the other;
+// each of the 16 dependent DFMAs then waited out the full pipe latency).
+template <int K>
+static __device__ __forceinline__ void exp_repro_many(const double* __restrict__ x, double* __restrict__ e)
 {
-    if (!(x > -745.2)) return (x == x) ? 0.0 : x;
-    if (x > 709.782712893384) return Num<double>::inf();
-    const double k = rint(__dmul_rn(x, 0x1.71547652b82fep+0));
-    double r = fma(-k, 0x1.62e42feep-1, x);
-    r = fma(-k, 0x1.a39ef35793c76p-33, r);
-    double p = 0x1.6124613a86d09p-33;
-    p = fma(p, r, 0x1.1eed8eff8d898p-29);
-    p = fma(p, r, 0x1.ae64567f544e4p-26);
-    p = fma(p, r, 0x1.27e4fb7789f5cp-22);
-    p = fma(p, r, 0x1.71de3a556c734p-19);
-    p = fma(p, r, 0x1.a01a01a01a01ap-16);
-    p = fma(p, r, 0x1.a01a01a01a01ap-13);
-    p = fma(p, r, 0x1.6c16c16c16c17p-10);
-    p = fma(p, r, 0x1.1111111111111p-7);
-    p = fma(p, r, 0x1.5555555555555p-5);
-    p = fma(p, r, 0x1.5555555555555p-3);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const int ki = (int)k;
-    if (ki >= -1000 && ki <= 1000) return __dmul_rn(p, __longlong_as_double((long long)(ki + 1023) << 52));
-    return ldexp(p, ki);
+    double xc[K], k[K], r[K], p[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) xc[j] = fmin(fmax(x[j], -746.0), 710.0);
+#pragma unroll
+    for (int j = 0; j < K; ++j) k[j] = rint(__dmul_rn(xc[j], kExpD[0]));
+#pragma unroll
+    for (int j = 0; j < K; ++j) r[j] = fma(-k[j], kExpD[1], xc[j]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) r[j] = fma(-k[j], kExpD[2], r[j]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) p[j] = kExpD[3];
+#pragma unroll
+    for (int i = 4; i < 17; ++i) {
+        const double c = kExpD[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = fma(p[j], r[j], c);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int ki = (int)k[j], h = ki >> 1;
+        const double s1 = __hiloint2double((h + 1023) << 20, 0);
+        const double s2 = __hiloint2double((ki - h + 1023) << 20, 0);
+        double v = __dmul_rn(__dmul_rn(p[j], s1), s2);
+        v = (x[j] > 709.782712893384) ? Num<double>::inf() : v;
+        e[j] = (x[j] > -745.2) ? v : ((x[j] == x[j]) ? 0.0 : x[j]);
+    }
 }
 
-static __device__ __forceinline__ float exp_repro_inl(float x)
+template <int K>
+static __device__ __forceinline__ void exp_repro_many(const float* __restrict__ x, float* __restrict__ e)
 {
-    if (!(x > -104.0f)) return (x == x) ? 0.0f : x;
-    if (x > 88.72284f) return Num<float>::inf();
-    const float k = rintf(__fmul_rn(x, 0x1.715476p+0f));
-    float r = fmaf(-k, 0x1.62e4p-1f, x);
-    r = fmaf(-k, 0x1.7f7d1cp-20f, r);
-    float p = 0x1.a01a02p-13f;
-    p = fmaf(p, r, 0x1.6c16c2p-10f);
-    p = fmaf(p, r, 0x1.111112p-7f);
-    p = fmaf(p, r, 0x1.555556p-5f);
-    p = fmaf(p, r, 0x1.555556p-3f);
-    p = fmaf(p, r, 0.5f);
-    p = fmaf(p, r, 1.0f);
-    p = fmaf(p, r, 1.0f);
-    const int ki = (int)k;
-    if (ki >= -120 && ki <= 120) return __fmul_rn(p, __int_as_float((ki + 127) << 23));
-    return ldexpf(p, ki);
+    float xc[K], k[K], r[K], p[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) xc[j] = fminf(fmaxf(x[j], -105.0f), 89.0f);
+#pragma unroll
+    for (int j = 0; j < K; ++j) k[j] = rintf(__fmul_rn(xc[j], kExpS[0]));
+#pragma unroll
+    for (int j = 0; j < K; ++j) r[j] = fmaf(-k[j], kExpS[1], xc[j]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) r[j] = fmaf(-k[j], kExpS[2], r[j]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) p[j] = kExpS[3];
+#pragma unroll
+    for (int i = 4; i < 11; ++i) {
+        const float c = kExpS[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = fmaf(p[j], r[j], c);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int ki = (int)k[j], h = ki >> 1;
+        const float s1 = __int_as_float((h + 127) << 23);
+        const float s2 = __int_as_float((ki - h + 127) << 23);
+        float v = __fmul_rn(__fmul_rn(p[j], s1), s2);
+        v = (x[j] > 88.72284f) ? Num<float>::inf() : v;
+        e[j] = (x[j] > -104.0f) ? v : ((x[j] == x[j]) ? 0.0f : x[j]);
+    }
 }
+
+static __device__ __forceinline__ double exp_repro_inl(double x) { double e; exp_repro_many<1>(&x, &e); return e; }
+static __device__ __forceinline__ float  exp_repro_inl(float x)  { float e;  exp_repro_many<1>(&x, &e); return e; }
 
 static __device__ __noinline__ double exp_repro(double x) { return exp_repro_inl(x); }
 static __device__ __noinline__ float  exp_repro(float x)  { return exp_repro_inl(x); }
