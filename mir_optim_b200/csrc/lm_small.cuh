@@ -128,16 +128,40 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
         ret.residual = Num<T>::inf(); ret.lambda = (T)0;
 
         // residual vector evaluation: out[k] = r_row(p) for this lane's rows, returns ||r||^2
+        // Exponential models: the exps of several rows go through one interleaved exp_repro_many call (about four
+        // independent chains in flight) -- same operations per row as Model::residual, bit for bit.
         auto eval = [&](const T (&p)[N], T (&out)[R]) -> T {
             const typename Model::Pre pre = Model::prepare(p);
             T part = (T)0;
+            if constexpr (Model::NE > 0) {
+                constexpr int NE = Model::NE;
+                constexpr int RB0 = NE >= 4 ? 1 : (NE >= 2 ? 2 : 4);
+                constexpr int RB = RB0 < R ? RB0 : R;
 #pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const int row = k * LANES + glane;
-                T r = (T)0;
-                if (row < m) r = Model::residual(pre, p, row, tt[k], yo[k]);
-                out[k] = r;
-                part += r * r;
+                for (int kb = 0; kb < R; kb += RB) {
+                    T ea[RB * NE], ee[RB * NE];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) Model::exp_args(pre, p, tt[kb + j], ea + j * NE);
+                    exp_repro_many<RB * NE>(ea, ee);
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const int row = (kb + j) * LANES + glane;
+                        T r;
+                        Model::finish_r(pre, p, tt[kb + j], yo[kb + j], ee + j * NE, r);
+                        r = row < m ? r : (T)0;
+                        out[kb + j] = r;
+                        part += r * r;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int row = k * LANES + glane;
+                    T r = (T)0;
+                    if (row < m) r = Model::residual(pre, p, row, tt[k], yo[k]);
+                    out[k] = r;
+                    part += r * r;
+                }
             }
             ++sEvals;
             return group_sum<LANES>(gmask, part);
@@ -219,10 +243,32 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         age = 0; ++sFresh;                                                   // LS:1010
                         if constexpr (!useFD) {                                              // LS:1011-1015
                             const typename Model::Pre pre = Model::prepare(x);
+                            if constexpr (Model::NE > 0) {
+                                constexpr int NE = Model::NE;
+                                constexpr int RB0 = NE >= 4 ? 1 : (NE >= 2 ? 2 : 4);
+                                constexpr int RB = RB0 < R ? RB0 : R;
 #pragma unroll
-                            for (int k = 0; k < R; ++k) {
-                                const int row = k * LANES + glane;
-                                if (row < m) Model::jacobian(pre, x, row, tt[k], J[k]);
+                                for (int kb = 0; kb < R; kb += RB) {
+                                    T ea[RB * NE], ee[RB * NE];
+#pragma unroll
+                                    for (int j = 0; j < RB; ++j) Model::exp_args(pre, x, tt[kb + j], ea + j * NE);
+                                    exp_repro_many<RB * NE>(ea, ee);
+#pragma unroll
+                                    for (int j = 0; j < RB; ++j) {
+                                        T Jrow[N];
+                                        Model::finish_j(pre, x, tt[kb + j], ee + j * NE, Jrow);
+                                        if ((kb + j) * LANES + glane < m) {
+#pragma unroll
+                                            for (int i = 0; i < N; ++i) J[kb + j][i] = Jrow[i];
+                                        }
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < R; ++k) {
+                                    const int row = k * LANES + glane;
+                                    if (row < m) Model::jacobian(pre, x, row, tt[k], J[k]);
+                                }
                             }
                             ret.gCalls += 1;
                         } else {                                                             // LS:1018-1049
@@ -241,12 +287,15 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                                 for (int k = 0; k < R; ++k) col[k] = (T)0;
                                 if (twh != (T)0) {
                                     T p[N], fp[R], fm[R];
+#pragma unroll 1
+                                    for (int sgn = 0; sgn < 2; ++sgn) {           // one eval site for f(x+h) and f(x-h): code size
+                                        T f[R];
 #pragma unroll
-                                    for (int i = 0; i < N; ++i) p[i] = (i == j) ? xph : x[i];
-                                    eval(p, fp);
+                                        for (int i = 0; i < N; ++i) p[i] = (i == j) ? (sgn ? xmh : xph) : x[i];
+                                        eval(p, f);
 #pragma unroll
-                                    for (int i = 0; i < N; ++i) p[i] = (i == j) ? xmh : x[i];
-                                    eval(p, fm);
+                                        for (int k = 0; k < R; ++k) { if (sgn) fm[k] = f[k]; else fp[k] = f[k]; }
+                                    }
                                     const T rt = rcp_ni(twh);
 #pragma unroll
                                     for (int k = 0; k < R; ++k) col[k] = (fp[k] - fm[k]) * rt;

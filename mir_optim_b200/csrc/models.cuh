@@ -23,7 +23,7 @@ template <class T> struct NoPre {};
 
 // r = (p0, 2 - p1)                                            least_squares.d:230-241
 template <class T> struct ModelLinear2 {
-    static constexpr int N = 2; static constexpr bool kHasData = false;
+    static constexpr int N = 2, NE = 0; static constexpr bool kHasData = false;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int row, T, T) { return row == 0 ? p[0] : sub_rn((T)2, p[1]); }
@@ -37,7 +37,7 @@ template <class T> struct ModelLinear2 {
 
 // Rosenbrock: r = (10 (p1 - p0^2), 1 - p0)                     least_squares.d:261-265, 295-301
 template <class T> struct ModelRosenbrock {
-    static constexpr int N = 2; static constexpr bool kHasData = false;
+    static constexpr int N = 2, NE = 0; static constexpr bool kHasData = false;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int row, T, T) {
@@ -53,7 +53,7 @@ template <class T> struct ModelRosenbrock {
 
 // r = sqrt(1 - (p0^2 + p1^2)), m = 1 < n = 2                   least_squares.d:427-430
 template <class T> struct ModelSqrtCircle {
-    static constexpr int N = 2; static constexpr bool kHasData = false;
+    static constexpr int N = 2, NE = 0; static constexpr bool kHasData = false;
     using Pre = NoPre<T>;
     __device__ static Pre prepare(const T (&)[N]) { return {}; }
     __device__ static T residual(const Pre&, const T (&p)[N], int, T, T) {
