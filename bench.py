@@ -128,6 +128,113 @@ def cpu_oracle_rate(wl, sample, nthreads=0):
     return sample / dt, threads, dt, res
 
 
+def _timed(torch, fn, reps):
+    """mean CUDA-event time (ms) of `reps` calls after one warm-up call."""
+    fn(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def secondary_batched(torch, eng, dev, workloads, rank):
+    """configs[2] (8-parameter sum of exponentials, FD Jacobian, double and float) and configs[4]a (batched n=64 BoxQP):
+    device-resident throughput of THIS rank's GPU (the batched paths shard without communication)."""
+    out = {}
+    for name, dt in (("c3_sumexp8_f64", np.float64), ("c3_sumexp8_f32", np.float32)):
+        B = 65536
+        wl = workloads.c3_sumexp8(B, dtype=dt, seed=3 + rank)
+        st = eng.settings(dt)
+        T = lambda v: torch.from_numpy(v).to(dev)
+        t, y, x0, l, u = T(wl.t), T(wl.y), T(wl.x0), T(wl.l), T(wl.u)
+        x = torch.empty_like(x0)
+        res = torch.empty(B * (32 if dt == np.float64 else 24), dtype=torch.uint8, device=dev)
+
+        def step():
+            x.copy_(x0)
+            eng.optimize_batched_device(st, wl.model, x, l, u, t=t, y=y, fd_jacobian=True, results=res)
+        ms = _timed(torch, step, 2)
+        ok = float(np.mean(eng.results_from_bytes(res, dt)["status"] >= 0))
+        out[name] = {"value": B / ms * 1e3, "unit": "fits/s per GPU", "batch": B, "m": 128, "n": 8, "jacobian": "finite differences",
+                     "ms": ms, "frac_status_ok": ok}
+    B, n = 100000, 64
+    g = torch.Generator(device=dev); g.manual_seed(5 + rank)
+    P = torch.empty(B, n, n, dtype=torch.float64, device=dev)
+    eye = 0.1 * torch.eye(n, dtype=torch.float64, device=dev)
+    for s0 in range(0, B, 4096):
+        e = min(B, s0 + 4096)
+        A = torch.randn(e - s0, 256, n, dtype=torch.float64, device=dev, generator=g)
+        P[s0:e] = torch.bmm(A.transpose(1, 2), A) / 256 + eye
+    q = torch.randn(B, n, dtype=torch.float64, device=dev, generator=g)
+    l = -2.0 * torch.rand(B, n, dtype=torch.float64, device=dev, generator=g)
+    u = 2.0 * torch.rand(B, n, dtype=torch.float64, device=dev, generator=g)
+    x = torch.zeros(B, n, dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev); iters = torch.empty(B, dtype=torch.int32, device=dev)
+    ms = _timed(torch, lambda: eng.solve_box_qp_batched_device(P, q, l, u, x, status, iters), 3)
+    lower = n * (n + 1) // 2 * 8 + 4 * n * 8 + 4
+    out["c5a_boxqp_n64_f64"] = {"value": B / ms * 1e3, "unit": "QP/s per GPU", "batch": B, "n": n, "ms": ms,
+                                "frac_solved": float((status == 0).double().mean().item()),
+                                "mean_boxcqp_iterations": float(iters.double().mean().item()),
+                                "active_fraction": float(((x == l) | (x == u)).double().mean().item()),
+                                "algorithmic_GBps": B * lower / ms / 1e6}
+    del P
+    return out
+
+
+def secondary_c4(torch, dist, eng, dev, workloads, sharding, rank, world, m=4_000_000):
+    """configs[3]: ONE problem, m = 4M residuals, n = 128, analytic Jacobian, rows sharded over all ranks; per accepted
+    step one NCCL all-reduce of [lower(J'J) | J'r] (8,384 doubles), per pass one 1-double all-reduce.  Strong scaling."""
+    comm = None
+    if world > 1:
+        comm = eng.nccl_comm_init(world, sharding.exchange_unique_id(eng, dist, rank), rank)
+    lo, hi = sharding.row_shard(m, rank, world)
+    wl = workloads.c4_gaussmix(m=m, row_slice=(lo, hi))
+    t = torch.from_numpy(wl.t).to(dev); y = torch.from_numpy(wl.y).to(dev)
+    st = eng.settings(np.float64)
+    best = None
+    for rep in range(3):
+        x = wl.x0[0].copy()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        r, stats = eng.optimize_sharded(st, wl.model, x, wl.l, wl.u, t, y, comm=comm, want_stats=True)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if rep > 0 and (best is None or dt < best[0]):
+            best = (dt, r, stats, x)
+    dt, r, stats, x = best
+    out = {"value": r.iterations / dt, "unit": "LM iterations/s (whole job)", "m": m, "n": wl.n, "rows_per_rank": hi - lo,
+           "solve_s": dt, "iterations": int(r.iterations), "passes": int(stats["passes"]), "passes_per_s": stats["passes"] / dt,
+           "status": int(r.status), "fCalls": int(r.fCalls), "gCalls": int(r.gCalls), "residual": float(r.residual),
+           "max_rel_err_vs_truth": float(np.max(np.abs(x - wl.truth[0]) / np.abs(wl.truth[0]))),
+           "timing": "wall clock around the blocking C-ABI call, device-synchronised, max over ranks, best of 2 after 1 warm-up",
+           "collective": "none (1 GPU)" if world == 1 else f"NCCL all-reduce over {world} ranks, 67 KB per accepted step + 8 B per pass"}
+    del t, y
+    if comm is not None:
+        eng.nccl_comm_destroy(comm)
+    if rank == 0:
+        # the dominant kernel of this path alone: J'J of this rank's rows on the FP64 tensor pipe (DMMA), J >> L2
+        rows = ((hi - lo) + 31) // 32 * 32
+        n = wl.n
+        J = torch.randn(rows, n + (n & 1), dtype=torch.float64, device=dev)
+        packed = torch.empty(n * (n + 1) // 2, dtype=torch.float64, device=dev)
+        ms = _timed(torch, lambda: eng.syrk_lower_device(J, n, packed), 5)
+        dmma = eng.lib.mir_b200_measure_peak_tflops(1, 5)
+        ach = rows * n * (n + 1) / ms / 1e9
+        out["roofline"] = {"bound": "tensor", "kernel": "syrk_dmma_kernel (FP64 mma.sync m8n8k4, TMA-fed)", "achieved": ach, "peak": dmma,
+                           "unit": "TFLOP/s", "frac": ach / dmma if dmma > 0 else None,
+                           "peak_source": "FP64 DMMA pipe measured live by mir_b200_measure_peak_tflops(1)",
+                           "algorithmic_flops_per_launch": rows * n * (n + 1), "kernel_ms": ms, "rows": rows,
+                           "J_read_GBps": rows * J.shape[1] * 8 / ms / 1e6}
+        del J
+    return out
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference algorithm (CPU oracle: restated LM/BOXCQP + real LAPACK ?posvx from
     OpenBLAS; the D reference itself cannot be built here -- no D compiler) on all host cores."""
@@ -167,6 +274,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=65536)
     ap.add_argument("--ref-step-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2]/[3]/[4] measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -267,6 +375,30 @@ def main():
     d2h = wl.x0.nbytes + res_e2e.nbytes
     assert np.array_equal(res_e2e, res_host) and np.array_equal(x_h.numpy(), x_d.cpu().numpy()), "e2e and resident paths disagree"
 
+    # ---------------- the other named configs (reported under "secondary"; every rank takes part) ----------------
+    secondary = None
+    if not args.no_secondary:
+        del t_d, y_d, x0_d, x_d, res_d
+        torch.cuda.empty_cache()
+        secondary = {}
+        try:
+            sec = secondary_batched(torch, eng, dev, workloads, rank)
+            for k, v in sec.items():                 # whole-job value = sum over ranks (independent problems, no collective)
+                tot = v["value"]
+                if world > 1:
+                    tt = torch.tensor([tot], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tt)
+                    tot = float(tt.item())
+                v["value_per_gpu_rank0"] = v["value"]; v["value"] = tot; v["unit"] = v["unit"].replace(" per GPU", " (whole job)")
+            secondary.update(sec)
+        except Exception as e:                       # noqa: BLE001 -- the headline line must still be printed
+            secondary["batched_error"] = repr(e)
+        try:
+            from mir_optim_b200 import sharding
+            secondary["c4_gaussmix_4Mx128_f64"] = secondary_c4(torch, dist if world > 1 else None, eng, dev, workloads, sharding, rank, world)
+        except Exception as e:                       # noqa: BLE001
+            secondary["c4_error"] = repr(e)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -279,7 +411,9 @@ def main():
     ach_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
     ach_gbs = ALGO_BYTES_PER_FIT * B / (kernel_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "fp64_fma", "kernel": "lm_small_kernel<ModelGauss4<double>, double, 32, 2>",
+        "bound": "fp64_fma",
+        "kernel": ("lm_tpp_kernel<ModelGauss4<double>, double, analytic J, v-list> (one thread per fit)" if B >= 16384
+                   else "lm_small_kernel<ModelGauss4<double>, double, 8 lanes per fit>"),
         "achieved": ach_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": ach_tf / dfma_peak if dfma_peak > 0 else None,
         "peak_source": "DFMA pipe measured live by mir_b200_measure_peak_tflops(0)",
         "traffic": None,
@@ -292,7 +426,8 @@ def main():
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
-            roofline["traffic"] = json.load(f).get("lm_small_gauss4_dram_bytes_per_launch")
+            roofline["traffic"] = json.load(f).get("lm_tpp_gauss4_1Mfits_dram_bytes_per_launch")
+            roofline["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-fit launch (ncu --set full), profiles/"
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -310,7 +445,7 @@ def main():
                        "parallelism": f"{world} GPU(s), problems split evenly, no collective"},
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_t / args.steps * 1e3},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

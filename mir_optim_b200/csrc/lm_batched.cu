@@ -11,7 +11,7 @@ namespace mirb200 {
 template <class T>
 static int batched_dev(const typename Num<T>::Settings* settings, const mir_model_desc* model, size_t batch, size_t m, size_t n,
                        T* x, const T* l, const T* u, size_t bound_stride, typename Num<T>::Result* results,
-                       mir_batch_stats* stats, cudaStream_t stream)
+                       mir_batch_stats* stats, cudaStream_t stream, const unsigned int* ready = nullptr)
 {
     clear_error();
     if (!settings || !model || (batch && (!x || !l || !u || !results))) { set_error("mir_optim_b200: null argument"); return MIR_B200_EINVAL; }
@@ -28,7 +28,7 @@ static int batched_dev(const typename Num<T>::Settings* settings, const mir_mode
 
     SmallBatchArgs a;
     a.t = model->t; a.y = model->y; a.x = x; a.l = l; a.u = u; a.results = results;
-    a.counter = counter; a.stats = stats; a.batch = batch; a.m = (unsigned)m;
+    a.counter = counter; a.ready = ready; a.stats = stats; a.batch = batch; a.m = (unsigned)m;
     a.bound_stride = (unsigned)bound_stride; a.flags = model->flags;
     rc = launch_small_model<T>(model->model, n, *settings, a, stream);
     cudaFreeAsync(counter, stream);
@@ -54,13 +54,34 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     const size_t bBytes = sizeof(T) * (bound_stride ? batch * bound_stride : n);
     const size_t rBytes = sizeof(Result) * batch;
 
-    cudaStream_t stream = nullptr;
-    MIRB200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // Pipeline.  ONE kernel launch for the whole batch (chunked launches lose ~15 % to queue drain at this grid size),
+    // enqueued BEFORE its inputs: the per-problem inputs follow on a copy stream in chunks of 65536 problems, each
+    // followed by a 4-byte watermark copy; a thread that pulls problem i from the queue waits until the watermark has
+    // passed i (wait_staged).  The copy engine runs ~3x ahead of the solve, so only the first chunk's transfer is exposed.
+    const size_t chunk = 65536;
+    const size_t nchunks = (batch + chunk - 1) / chunk;
+    cudaStream_t cs = nullptr, ps = nullptr;
+    cudaEvent_t ev = nullptr;
+    unsigned int* h_wm = nullptr;
+    rc = MIR_B200_OK;
+    auto CK = [&](cudaError_t err, const char* what) { if (rc == MIR_B200_OK) rc = check_cuda(err, what); };
+    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
+    CK(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking), "cudaStreamCreate");
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+    CK(cudaMallocHost((void**)&h_wm, sizeof(unsigned int) * (nchunks + 1)), "cudaMallocHost(watermarks)");
+    auto cleanup = [&]() {
+        if (cs) cudaStreamDestroy(cs);
+        if (ps) cudaStreamDestroy(ps);
+        if (ev) cudaEventDestroy(ev);
+        if (h_wm) cudaFreeHost(h_wm);
+    };
+    if (rc != MIR_B200_OK) { cleanup(); return rc; }
+
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t total = align(tBytes) + align(yBytes) + align(xBytes) + 2 * align(bBytes) + align(rBytes) + align(sizeof(mir_batch_stats));
+    const size_t total = align(tBytes) + align(yBytes) + align(xBytes) + 2 * align(bBytes) + align(rBytes) + align(sizeof(mir_batch_stats)) + 256;
     char* base = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&base, total, stream);
-    if (e != cudaSuccess) { cudaStreamDestroy(stream); return check_cuda(e, "cudaMallocAsync(batch buffers)"); }
+    cudaError_t e = cudaMallocAsync((void**)&base, total, cs);
+    if (e != cudaSuccess) { cleanup(); return check_cuda(e, "cudaMallocAsync(batch buffers)"); }
     char* p = base;
     T* dt = (T*)p; p += align(tBytes);
     T* dy = (T*)p; p += align(yBytes);
@@ -68,30 +89,55 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     T* dl = (T*)p; p += align(bBytes);
     T* du = (T*)p; p += align(bBytes);
     Result* dr = (Result*)p; p += align(rBytes);
-    mir_batch_stats* ds = (mir_batch_stats*)p;
+    mir_batch_stats* ds = (mir_batch_stats*)p; p += align(sizeof(mir_batch_stats));
+    unsigned int* d_ready = (unsigned int*)p;
 
-    rc = MIR_B200_OK;
-    auto CK = [&](cudaError_t err, const char* what) { if (rc == MIR_B200_OK) rc = check_cuda(err, what); };
-    if (tBytes) CK(cudaMemcpyAsync(dt, model->t, tBytes, cudaMemcpyHostToDevice, stream), "H2D t");
-    if (yBytes) CK(cudaMemcpyAsync(dy, model->y, yBytes, cudaMemcpyHostToDevice, stream), "H2D y");
-    CK(cudaMemcpyAsync(dx, x, xBytes, cudaMemcpyHostToDevice, stream), "H2D x");
-    CK(cudaMemcpyAsync(dl, l, bBytes, cudaMemcpyHostToDevice, stream), "H2D l");
-    CK(cudaMemcpyAsync(du, u, bBytes, cudaMemcpyHostToDevice, stream), "H2D u");
-    if (stats) CK(cudaMemsetAsync(ds, 0, sizeof(mir_batch_stats), stream), "memset stats");
+    // shared inputs, counters and the watermark (0 = nothing staged), then the kernel
+    if (tBytes && !per) CK(cudaMemcpyAsync(dt, model->t, tBytes, cudaMemcpyHostToDevice, cs), "H2D t");
+    if (!bound_stride) {
+        CK(cudaMemcpyAsync(dl, l, bBytes, cudaMemcpyHostToDevice, cs), "H2D l");
+        CK(cudaMemcpyAsync(du, u, bBytes, cudaMemcpyHostToDevice, cs), "H2D u");
+    }
+    if (stats) CK(cudaMemsetAsync(ds, 0, sizeof(mir_batch_stats), cs), "memset stats");
+    CK(cudaMemsetAsync(d_ready, 0, sizeof(unsigned int), cs), "memset watermark");
+    CK(cudaEventRecord(ev, cs), "cudaEventRecord");
+    CK(cudaStreamWaitEvent(ps, ev, 0), "cudaStreamWaitEvent");
+    bool launched = false;
     if (rc == MIR_B200_OK) {
         mir_model_desc dm = *model;
         dm.t = tBytes ? dt : nullptr; dm.y = yBytes ? dy : nullptr;
-        rc = batched_dev<T>(settings, &dm, batch, m, n, dx, dl, du, bound_stride, dr, stats ? ds : nullptr, stream);
+        rc = batched_dev<T>(settings, &dm, batch, m, n, dx, dl, du, bound_stride, dr, stats ? ds : nullptr, cs, d_ready);
+        launched = rc == MIR_B200_OK;
+    }
+    // the per-problem inputs, chunk by chunk, behind the running kernel
+    size_t c = 0;
+    for (size_t lo = 0; lo < batch && rc == MIR_B200_OK; lo += chunk, ++c) {
+        const size_t nb = (lo + chunk <= batch) ? chunk : batch - lo;
+        if (tBytes && per) CK(cudaMemcpyAsync(dt + lo * m, static_cast<const T*>(model->t) + lo * m, sizeof(T) * nb * m, cudaMemcpyHostToDevice, ps), "H2D t");
+        if (yBytes) CK(cudaMemcpyAsync(dy + lo * m, static_cast<const T*>(model->y) + lo * m, sizeof(T) * nb * m, cudaMemcpyHostToDevice, ps), "H2D y");
+        CK(cudaMemcpyAsync(dx + lo * n, x + lo * n, sizeof(T) * nb * n, cudaMemcpyHostToDevice, ps), "H2D x");
+        if (bound_stride) {
+            CK(cudaMemcpyAsync(dl + lo * bound_stride, l + lo * bound_stride, sizeof(T) * nb * bound_stride, cudaMemcpyHostToDevice, ps), "H2D l");
+            CK(cudaMemcpyAsync(du + lo * bound_stride, u + lo * bound_stride, sizeof(T) * nb * bound_stride, cudaMemcpyHostToDevice, ps), "H2D u");
+        }
+        h_wm[c] = (unsigned int)(lo + nb);
+        CK(cudaMemcpyAsync(d_ready, &h_wm[c], sizeof(unsigned int), cudaMemcpyHostToDevice, ps), "H2D watermark");
+    }
+    if (launched && rc != MIR_B200_OK) {             // a copy failed behind a running kernel: release the waiters
+        h_wm[nchunks] = 0xffffffffu;
+        cudaMemcpyAsync(d_ready, &h_wm[nchunks], sizeof(unsigned int), cudaMemcpyHostToDevice, ps);
     }
     if (rc == MIR_B200_OK) {
-        CK(cudaMemcpyAsync(x, dx, xBytes, cudaMemcpyDeviceToHost, stream), "D2H x");
-        CK(cudaMemcpyAsync(results, dr, rBytes, cudaMemcpyDeviceToHost, stream), "D2H results");
-        if (stats) CK(cudaMemcpyAsync(stats, ds, sizeof(mir_batch_stats), cudaMemcpyDeviceToHost, stream), "D2H stats");
+        CK(cudaMemcpyAsync(x, dx, xBytes, cudaMemcpyDeviceToHost, cs), "D2H x");
+        CK(cudaMemcpyAsync(results, dr, rBytes, cudaMemcpyDeviceToHost, cs), "D2H results");
+        if (stats) CK(cudaMemcpyAsync(stats, ds, sizeof(mir_batch_stats), cudaMemcpyDeviceToHost, cs), "D2H stats");
     }
-    cudaFreeAsync(base, stream);
-    cudaError_t se = cudaStreamSynchronize(stream);
+    cudaError_t se = cudaStreamSynchronize(ps);
+    if (rc == MIR_B200_OK) rc = check_cuda(se, "batched LM input staging");
+    cudaFreeAsync(base, cs);
+    se = cudaStreamSynchronize(cs);
     if (rc == MIR_B200_OK) rc = check_cuda(se, "batched LM kernel");
-    cudaStreamDestroy(stream);
+    cleanup();
     return rc;
 }
 

@@ -32,12 +32,31 @@ struct SmallBatchArgs {
     const void* u;
     void*       results;    // Result[batch]
     unsigned int* counter;         // work queue head (zeroed by the launcher); batch < 2^32 per launch
+    const unsigned int* ready;     // null, or a watermark: problems [0, *ready) have been staged into device memory.  The
+                                   // host-pointer entry launches the kernel first and copies the inputs behind it in chunks,
+                                   // bumping the watermark after each chunk, so the transfer overlaps the solve.
     mir_batch_stats* stats; // may be null
     unsigned long long batch;
     unsigned m;
     unsigned bound_stride;
     unsigned flags;         // MIR_MODEL_* flags
 };
+
+// Blocks until problem `idx` has been staged (see SmallBatchArgs::ready).  The watermark is written by the copy engine
+// (stream-ordered after the chunk's data), read here with acquire semantics at gpu scope.  Chunks are multiples of
+// 65536 problems, so no cache line of any input array straddles staged and unstaged data.  The spin is bounded
+// (~20 s) so that a failed host-side copy cannot hang the GPU.
+__device__ __forceinline__ void wait_staged(const unsigned int* ready, unsigned int idx)
+{
+    if (!ready) return;
+    unsigned spins = 0;
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+        if (v > idx || ++spins > 20000000u) break;
+        __nanosleep(1000);
+    }
+}
 
 #ifndef MIRB200_MINBLOCKS
 #define MIRB200_MINBLOCKS 1
@@ -95,7 +114,10 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
 
     for (;;) {
         unsigned int prob32 = 0;
-        if (glane == 0) prob32 = atomicAdd(args.counter, 1u);
+        if (glane == 0) {
+            prob32 = atomicAdd(args.counter, 1u);
+            if (prob32 < args.batch) wait_staged(args.ready, prob32);
+        }
         prob32 = __shfl_sync(gmask, prob32, 0, LANES);
         if (prob32 >= args.batch) break;
         const unsigned long long prob = prob32;
@@ -128,40 +150,16 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
         ret.residual = Num<T>::inf(); ret.lambda = (T)0;
 
         // residual vector evaluation: out[k] = r_row(p) for this lane's rows, returns ||r||^2
-        // Exponential models: the exps of several rows go through one interleaved exp_repro_many call (about four
-        // independent chains in flight) -- same operations per row as Model::residual, bit for bit.
         auto eval = [&](const T (&p)[N], T (&out)[R]) -> T {
             const typename Model::Pre pre = Model::prepare(p);
             T part = (T)0;
-            if constexpr (Model::NE > 0) {
-                constexpr int NE = Model::NE;
-                constexpr int RB0 = NE >= 4 ? 1 : (NE >= 2 ? 2 : 4);
-                constexpr int RB = RB0 < R ? RB0 : R;
 #pragma unroll
-                for (int kb = 0; kb < R; kb += RB) {
-                    T ea[RB * NE], ee[RB * NE];
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) Model::exp_args(pre, p, tt[kb + j], ea + j * NE);
-                    exp_repro_many<RB * NE>(ea, ee);
-#pragma unroll
-                    for (int j = 0; j < RB; ++j) {
-                        const int row = (kb + j) * LANES + glane;
-                        T r;
-                        Model::finish_r(pre, p, tt[kb + j], yo[kb + j], ee + j * NE, r);
-                        r = row < m ? r : (T)0;
-                        out[kb + j] = r;
-                        part += r * r;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    const int row = k * LANES + glane;
-                    T r = (T)0;
-                    if (row < m) r = Model::residual(pre, p, row, tt[k], yo[k]);
-                    out[k] = r;
-                    part += r * r;
-                }
+            for (int k = 0; k < R; ++k) {
+                const int row = k * LANES + glane;
+                T r = (T)0;
+                if (row < m) r = Model::residual(pre, p, row, tt[k], yo[k]);
+                out[k] = r;
+                part += r * r;
             }
             ++sEvals;
             return group_sum<LANES>(gmask, part);
@@ -243,32 +241,10 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         age = 0; ++sFresh;                                                   // LS:1010
                         if constexpr (!useFD) {                                              // LS:1011-1015
                             const typename Model::Pre pre = Model::prepare(x);
-                            if constexpr (Model::NE > 0) {
-                                constexpr int NE = Model::NE;
-                                constexpr int RB0 = NE >= 4 ? 1 : (NE >= 2 ? 2 : 4);
-                                constexpr int RB = RB0 < R ? RB0 : R;
 #pragma unroll
-                                for (int kb = 0; kb < R; kb += RB) {
-                                    T ea[RB * NE], ee[RB * NE];
-#pragma unroll
-                                    for (int j = 0; j < RB; ++j) Model::exp_args(pre, x, tt[kb + j], ea + j * NE);
-                                    exp_repro_many<RB * NE>(ea, ee);
-#pragma unroll
-                                    for (int j = 0; j < RB; ++j) {
-                                        T Jrow[N];
-                                        Model::finish_j(pre, x, tt[kb + j], ee + j * NE, Jrow);
-                                        if ((kb + j) * LANES + glane < m) {
-#pragma unroll
-                                            for (int i = 0; i < N; ++i) J[kb + j][i] = Jrow[i];
-                                        }
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < R; ++k) {
-                                    const int row = k * LANES + glane;
-                                    if (row < m) Model::jacobian(pre, x, row, tt[k], J[k]);
-                                }
+                            for (int k = 0; k < R; ++k) {
+                                const int row = k * LANES + glane;
+                                if (row < m) Model::jacobian(pre, x, row, tt[k], J[k]);
                             }
                             ret.gCalls += 1;
                         } else {                                                             // LS:1018-1049
@@ -287,15 +263,12 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                                 for (int k = 0; k < R; ++k) col[k] = (T)0;
                                 if (twh != (T)0) {
                                     T p[N], fp[R], fm[R];
-#pragma unroll 1
-                                    for (int sgn = 0; sgn < 2; ++sgn) {           // one eval site for f(x+h) and f(x-h): code size
-                                        T f[R];
 #pragma unroll
-                                        for (int i = 0; i < N; ++i) p[i] = (i == j) ? (sgn ? xmh : xph) : x[i];
-                                        eval(p, f);
+                                    for (int i = 0; i < N; ++i) p[i] = (i == j) ? xph : x[i];
+                                    eval(p, fp);
 #pragma unroll
-                                        for (int k = 0; k < R; ++k) { if (sgn) fm[k] = f[k]; else fp[k] = f[k]; }
-                                    }
+                                    for (int i = 0; i < N; ++i) p[i] = (i == j) ? xmh : x[i];
+                                    eval(p, fm);
                                     const T rt = rcp_ni(twh);
 #pragma unroll
                                     for (int k = 0; k < R; ++k) col[k] = (fp[k] - fm[k]) * rt;

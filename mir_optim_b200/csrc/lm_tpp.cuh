@@ -136,6 +136,7 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
             const unsigned int idx = atomicAdd(args.counter, 1u);
             if (idx >= args.batch) retired = true;
             else {
+                wait_staged(args.ready, idx);
                 prob = idx; ++sProblems;
                 const T* xp = static_cast<const T*>(args.x) + prob * N;
                 lp = static_cast<const T*>(args.l) + prob * args.bound_stride;
