@@ -259,10 +259,29 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "fits/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} of the 2^20 fits per step, one forked worker process per core over problems, OpenBLAS 1 thread/worker; host has {cores} logical cores"},
             "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _own_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries print to fd 1 meanwhile (e.g. NCCL's version banner)
+    is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    _own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -446,7 +465,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_t / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

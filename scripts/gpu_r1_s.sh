@@ -1,0 +1,7 @@
+#!/bin/bash
+# 2-GPU bench through torchrun, exactly as the driver launches it
+mkdir -p gpurun_out
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+echo "exit $?"; tail -c 4000 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err
+echo "exit $?"; tail -c 1500 gpurun_out/bench_ref_n2.json
