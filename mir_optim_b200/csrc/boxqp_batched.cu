@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(NT) boxqp_cta_kernel(const QPBatchArgs<T> a)
         int st;
         if (A_SMEM) {
             auto P = [&](int i, int j) -> T { return sA[i * lda + j]; };
-            st = cta_boxqp<T, NT>(a.st, n, P, sq, sl, su, sx, w, iters, solves);
+            st = cta_boxqp<T, NT, false>(a.st, n, P, sq, sl, su, sx, w, iters, solves);
         } else {
             auto P = [&](int i, int j) -> T { return __ldg(Pg + (size_t)i * n + j); };
-            st = cta_boxqp<T, NT>(a.st, n, P, sq, sl, su, sx, w, iters, solves);
+            st = cta_boxqp<T, NT, false>(a.st, n, P, sq, sl, su, sx, w, iters, solves);
         }
         __syncthreads();
         for (int i = tid; i < n; i += NT) a.x[(size_t)prob * n + i] = sx[i];

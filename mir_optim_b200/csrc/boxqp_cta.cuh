@@ -44,18 +44,21 @@ template <class T> struct CtaQPScratch {
     T* la;       // multipliers of lower bounds
     T* mu;       // multipliers of upper bounds
     T* red;      // 32 reduction slots
+    T* blk;      // blocked factorisation / solve staging: panel nmaxPad x 9, diagonal tile 8 x 9, 8 broadcast values
     int* idx;    // free-index list (ascending)
     signed char* flag;   // -1 lower, 0 free, +1 upper (boxcqp.d:153-158)
     int ldf;
     __host__ __device__ static size_t bytes(int nmax) {
-        return sizeof(T) * ((size_t)nmax * (nmax + 8) + 7 * (size_t)nmax + 32) + sizeof(int) * nmax + ((nmax + 15) & ~15);
+        return sizeof(T) * ((size_t)nmax * (nmax + 8) + 7 * (size_t)nmax + 32 + blk_elems(nmax)) + sizeof(int) * nmax + ((nmax + 15) & ~15);
+    }
+    __host__ __device__ static size_t blk_elems(int nmax) { return (size_t)((nmax + 7) & ~7) * 9 + 72 + 8;
     }
     __device__ void carve(void* base, int nmax) {
         ldf = nmax + 8;
         T* p = static_cast<T*>(base);
         F = p; p += (size_t)nmax * ldf;
         sc = p; p += nmax; dinv = p; p += nmax; b = p; p += nmax; sx = p; p += nmax; r = p; p += nmax;
-        la = p; p += nmax; mu = p; p += nmax; red = p; p += 32;
+        la = p; p += nmax; mu = p; p += nmax; red = p; p += 32; blk = p; p += blk_elems(nmax);
         idx = reinterpret_cast<int*>(p);
         flag = reinterpret_cast<signed char*>(idx + nmax);
     }
@@ -84,9 +87,180 @@ __device__ __forceinline__ void cta_ldl_solve(int s, const T* F, int ldf, const 
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Blocked variants (8 x 8 tiles).  They perform, for every matrix / vector element, the SAME floating-point operations
+// in the SAME order as the column-by-column loops they replace (an element (i,k) is updated with pivots p = 0, 1, ...
+// ascending; the blocking only groups eight pivots between barriers), so the results are bit-identical -- but the
+// trailing matrix lives in registers (one lower-triangular 8 x 8 tile per thread), and a factorisation needs 3 CTA
+// barriers per eight columns instead of one per column with all operands in shared memory.  ncu, round 1: the
+// column loop made large_ctl_mid_kernel (n = 128) 0.31-0.47 ms per LM pass, 4 warps mostly waiting at barriers.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT> __host__ __device__ constexpr bool cta_blocked_ok(int s) { return ((s + 7) / 8) * ((s + 7) / 8 + 1) / 2 <= NT; }
+
+// LDL^T (square-root free), lower triangle of the matrix in F on entry, factor (unscaled Schur columns) in F and the
+// reciprocal pivots in dinv on exit.  Returns 0 or the 1-based index of the first pivot <= 0 (uniform over the CTA).
+template <class T, int NT>
+__device__ int cta_ldl_factor_blocked(int s, T* F, int ldf, T* dinv, T* blk)
+{
+    const int tid = threadIdx.x;
+    const int nb = (s + 7) >> 3;
+    T* Pn = blk;                                   // panel: row i at Pn[i * 9 + p], p < 8
+    T* Dg = blk + (size_t)nb * 8 * 9;              // diagonal tile: Dg[k * 9 + p]
+    __shared__ int s_info;
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+    const int tj = tid - ti * (ti + 1) / 2;
+    const bool owner = ti < nb;                    // this thread owns tile (ti, tj), ti >= tj
+    T a[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int i = 8 * ti + r, k = 8 * tj + c;
+            a[r][c] = (owner && i < s && k <= i) ? F[i * ldf + k] : ((i == k) ? (T)1 : (T)0);      // identity padding
+        }
+    if (tid == 0) s_info = 0;
+    __syncthreads();
+
+    for (int jt = 0; jt < nb; ++jt) {
+        // 1. the diagonal tile: plain right-looking LDL^T in registers
+        if (owner && ti == jt && tj == jt) {
+            int info = 0;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const T d = a[p][p];
+                if (info == 0 && 8 * jt + p < s && d <= (T)0) info = 8 * jt + p + 1;     // a NaN pivot passes, as in OpenBLAS' potrf
+                const T inv = (T)1 / d;
+                if (8 * jt + p < s) dinv[8 * jt + p] = inv;
+                Dg[64 + 8 + p] = inv;                 // (Dg has 72 + 8 slots: the 8 reciprocal pivots of this block)
+#pragma unroll
+                for (int i = p + 1; i < 8; ++i) {
+                    const T li = a[i][p] * inv;
+#pragma unroll
+                    for (int k = p + 1; k <= i; ++k) a[i][k] -= li * a[k][p];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) {
+                    Dg[r * 9 + c] = a[r][c];
+                    if (8 * jt + r < s) F[(8 * jt + r) * ldf + 8 * jt + c] = a[r][c];
+                }
+            if (info) s_info = info;
+        }
+        __syncthreads();
+        if (s_info) return s_info;
+        // 2. the panel below it: columns of the block, left to right
+        if (owner && tj == jt && ti > jt) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const T inv = Dg[64 + 8 + p];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const T li = a[r][p] * inv;
+#pragma unroll
+                    for (int k = p + 1; k < 8; ++k) a[r][k] -= li * Dg[k * 9 + p];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    Pn[(8 * ti + r) * 9 + c] = a[r][c];
+                    if (8 * ti + r < s) F[(8 * ti + r) * ldf + 8 * jt + c] = a[r][c];
+                }
+        }
+        __syncthreads();
+        // 3. the trailing tiles: eight rank-1 updates from the panel, operands in registers
+        if (owner && tj > jt) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const T inv = Dg[64 + 8 + p];
+                T li[8], ck[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { li[r] = Pn[(8 * ti + r) * 9 + p] * inv; ck[r] = Pn[(8 * tj + r) * 9 + p]; }
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a[r][c] -= li[r] * ck[c];
+            }
+        }
+        __syncthreads();
+    }
+    return 0;
+}
+
+// L D L^T solve, blocked by eight columns: the 8 x 8 diagonal part runs in one thread, the rest is row-parallel.
+// Same operations per element and the same order as cta_ldl_solve.
+template <class T, int NT>
+__device__ __forceinline__ void cta_ldl_solve_blocked(int s, const T* F, int ldf, const T* dinv, T* v, T* blk)
+{
+    const int tid = threadIdx.x;
+    const int nb = (s + 7) >> 3;
+    T* bc = blk;                                   // 8 broadcast values
+    __syncthreads();
+    for (int jb = 0; jb < nb; ++jb) {              // forward: t_j = v_j dinv_j, v_i -= F_ij t_j, j ascending
+        const int j0 = 8 * jb;
+        if (tid == 0) {
+            T vv[8], tt[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) vv[p] = (j0 + p < s) ? v[j0 + p] : (T)0;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                tt[p] = (j0 + p < s) ? vv[p] * dinv[j0 + p] : (T)0;
+#pragma unroll
+                for (int i = p + 1; i < 8; ++i) if (j0 + i < s) vv[i] -= F[(j0 + i) * ldf + j0 + p] * tt[p];
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) { bc[p] = tt[p]; if (j0 + p < s) v[j0 + p] = vv[p]; }
+        }
+        __syncthreads();
+        for (int i = j0 + 8 + tid; i < s; i += NT) {
+            T vi = v[i];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) vi -= F[i * ldf + j0 + p] * bc[p];
+            v[i] = vi;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < s; i += NT) v[i] *= dinv[i];     // D^-1
+    __syncthreads();
+    for (int jb = nb - 1; jb >= 0; --jb) {         // backward: v_i -= F_ji dinv_i x_j, j descending
+        const int j0 = 8 * jb;
+        if (tid == 0) {
+            T vv[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) vv[p] = (j0 + p < s) ? v[j0 + p] : (T)0;
+#pragma unroll
+            for (int p = 7; p >= 1; --p) {
+                if (j0 + p < s) {
+                    const T xj = vv[p];
+#pragma unroll
+                    for (int i = 0; i < p; ++i) vv[i] -= F[(j0 + p) * ldf + j0 + i] * dinv[j0 + i] * xj;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) { bc[p] = vv[p]; if (j0 + p < s) v[j0 + p] = vv[p]; }
+        }
+        __syncthreads();
+        for (int i = tid; i < j0; i += NT) {
+            T vi = v[i];
+            const T di = dinv[i];
+#pragma unroll
+            for (int p = 7; p >= 0; --p) if (j0 + p < s) vi -= F[(j0 + p) * ldf + i] * di * bc[p];
+            v[i] = vi;
+        }
+        __syncthreads();
+    }
+}
+
 // A(a, c) for a >= c returns the (unscaled) entry of the s x s system.  b: rhs (overwritten by its
 // scaled copy), x: solution.  Returns LAPACK info (0, or k>0 = breakdown at pivot k), uniform over the CTA.
-template <class T, int NT, class AGet>
+// BLK: use the blocked register-tiled factorisation / solves.  They win when ONE CTA works alone and latency is all
+// that matters (the LM control kernel, n = 128: 0.47 -> 0.22 ms); the batched BoxQP kernel, with two CTAs per SM
+// competing for issue slots, is faster with the all-threads column loop (measured 1.35 M vs 1.17 M QP/s at n = 64).
+template <class T, int NT, bool BLK, class AGet>
 __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
 {
     const int tid = threadIdx.x;
@@ -115,9 +289,14 @@ __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
     __syncthreads();
 
     // factorisation: right-looking, square-root free.  Column j keeps its unscaled Schur values.
+    const bool blocked = BLK && cta_blocked_ok<NT>(s);
+    if (blocked) {
+        const int info = cta_ldl_factor_blocked<T, NT>(s, F, ldf, w.dinv, w.blk);
+        if (info) return info;
+    }
     constexpr int TK = 8, TI = NT / TK;
     const int tx = tid % TK, ty = tid / TK;
-    for (int j = 0; j < s; ++j) {
+    for (int j = 0; j < (blocked ? 0 : s); ++j) {
         const T d = F[j * ldf + j];
         if (d <= (T)0) return j + 1;     // uniform (every thread reads the same d).  A NaN pivot passes, as in OpenBLAS' potrf
         const T inv = (T)1 / d;
@@ -130,7 +309,8 @@ __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
     }
 
     for (int a = tid; a < s; a += NT) x[a] = b[a];
-    cta_ldl_solve<T, NT>(s, F, ldf, w.dinv, x);
+    if (blocked) cta_ldl_solve_blocked<T, NT>(s, F, ldf, w.dinv, x, w.blk);
+    else cta_ldl_solve<T, NT>(s, F, ldf, w.dinv, x);
 
     // ?porfs
     const T eps = Num<T>::lapack_eps();
@@ -152,7 +332,8 @@ __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
         }
         const T berr = cta_reduce_max<T, NT>(q, w.red);
         if (berr > eps && (T)2 * berr <= lstres && count <= 5) {
-            cta_ldl_solve<T, NT>(s, F, ldf, w.dinv, w.r);
+            if (blocked) cta_ldl_solve_blocked<T, NT>(s, F, ldf, w.dinv, w.r, w.blk);
+            else cta_ldl_solve<T, NT>(s, F, ldf, w.dinv, w.r);
             for (int a = tid; a < s; a += NT) x[a] += w.r[a];
             __syncthreads();
             lstres = berr;
@@ -167,7 +348,7 @@ __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
 
 // P(i, j) for i >= j: lower triangle of the QP matrix.  q, l, u, x: length n (shared or global).
 // Returns mir_box_qp_status (uniform).  iterations: BOXCQP main-loop count, solves: posvx calls.
-template <class T, int NT, class PGet>
+template <class T, int NT, bool BLK, class PGet>
 __device__ int cta_boxqp(const typename Num<T>::QPSettings& st, int n, PGet P, const T* q, const T* l, const T* u, T* x,
                          CtaQPScratch<T>& w, unsigned& iterations, unsigned& solves)
 {
@@ -178,7 +359,7 @@ __device__ int cta_boxqp(const typename Num<T>::QPSettings& st, int n, PGet P, c
     for (int i = tid; i < n; i += NT) w.b[i] = -q[i];                          // boxcqp.d:191
     __syncthreads();
     ++solves;
-    if (cta_posvx<T, NT>(n, P, w, w.b, x) != 0) return mir_qp_numericError;    // boxcqp.d:194-213
+    if (cta_posvx<T, NT, BLK>(n, P, w, w.b, x) != 0) return mir_qp_numericError;    // boxcqp.d:194-213
 
     bool out = false;                                                          // boxcqp.d:216-219
     for (int i = tid; i < n; i += NT) out = out || !(l[i] <= x[i] && x[i] <= u[i]);
@@ -226,7 +407,7 @@ __device__ int cta_boxqp(const typename Num<T>::QPSettings& st, int n, PGet P, c
             ++solves;
             const int* idx = w.idx;
             auto Asub = [&](int a, int c) -> T { return P(idx[a], idx[c]); };  // idx ascending: a >= c => idx[a] >= idx[c]
-            if (cta_posvx<T, NT>(s, Asub, w, w.b, w.sx) != 0) return mir_qp_numericError;   // boxcqp.d:310-324
+            if (cta_posvx<T, NT, BLK>(s, Asub, w, w.b, w.sx) != 0) return mir_qp_numericError;   // boxcqp.d:310-324
             for (int a = tid; a < s; a += NT) x[w.idx[a]] = w.sx[a];           // boxcqp.d:327-329
             __syncthreads();
         }

@@ -240,7 +240,7 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
     for (int i = 0; i < n; ++i) { h->x[i] = x[i]; h->xt[i] = x[i]; h->l[i] = l[i]; h->u[i] = u[i]; }
     MIRB200_CUDA(cudaMemcpyAsync(d_ctl, h.get(), sizeof(Ctl), cudaMemcpyHostToDevice, stream));
 
-    const size_t ctlSmem = ((CtaQPScratch<T>::bytes(n) + 15) & ~(size_t)15) + sizeof(T) * 4 * (size_t)n;
+    const size_t ctlSmem = ((CtaQPScratch<T>::bytes(n) + 15) & ~(size_t)15) + sizeof(T) * (4 * (size_t)n + (size_t)np);   // + packed lower J^T J
     MIRB200_CUDA(cudaFuncSetAttribute(large_ctl_mid_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctlSmem));
     const size_t jacSmem = sizeof(T) * LARGE_TILE * (size_t)(ldj + 1);
     if (kDouble) MIRB200_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM_BYTES));

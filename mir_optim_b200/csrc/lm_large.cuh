@@ -32,7 +32,7 @@ namespace mirb200 {
 constexpr int LARGE_NMAX = 128;
 constexpr int LARGE_NP_MAX = LARGE_NMAX * (LARGE_NMAX + 1) / 2;
 constexpr int LARGE_TILE = 32;       // rows per Jacobian tile
-constexpr int LARGE_CTL_THREADS = 128;
+constexpr int LARGE_CTL_THREADS = 256;      // >= 136 = lower-triangular 8 x 8 tiles of a 128 x 128 system (cta_ldl_factor_blocked)
 
 enum { JAC_NONE = 0, JAC_BROYDEN = 1, JAC_FRESH = 2 };
 
@@ -373,20 +373,18 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeC
     w.carve(ctl_smem, n);
     T* vec = reinterpret_cast<T*>(ctl_smem + ((CtaQPScratch<T>::bytes(n) + 15) & ~(size_t)15));
     T* sq = vec; T* sl = vec + n; T* su = vec + 2 * n; T* sx = vec + 3 * n;
+    T* sA = vec + 4 * n;                             // packed lower J^T J (undamped), staged once: every P(i, j) below is a shared load
     __shared__ int s_flag;
+    const int np = n * (n + 1) / 2;
 
+    for (int e = tid; e < np; e += NT) sA[e] = c->packed[e];
     if (c->jacMode != JAC_NONE) {
-        const int np = n * (n + 1) / 2;
-        for (int e = tid; e < n * n; e += NT) {
-            const int i = e / n, j = e - i * n;
-            if (j <= i) c->JJ[i * LARGE_NMAX + j] = c->packed[i * (i + 1) / 2 + j];
-        }
-        for (int k = tid; k < n; k += NT) c->Jy[k] = c->packed[np + k];
+        for (int k = tid; k < n; k += NT) { const T g = c->packed[np + k]; c->Jy[k] = g; sq[k] = g; }
         __syncthreads();
         if (tid == 0) {                                                                            // LS:1053-1062
             // iamax: first index of max |.|; NaN never wins unless it is element 0 (reference BLAS behaviour)
-            T best = t_abs(c->Jy[0]); T sel = c->Jy[0];
-            for (int k = 1; k < n; ++k) { const T v = t_abs(c->Jy[k]); if (v > best) { best = v; sel = c->Jy[k]; } }
+            T best = t_abs(sq[0]); T sel = sq[0];
+            for (int k = 1; k < n; ++k) { const T v = t_abs(sq[k]); if (v > best) { best = v; sel = sq[k]; } }
             int f = 0;
             if (!(t_abs(sel) > c->st.gradTolerance)) {
                 if (c->age == 0) { c->status = mir_ls_gConverged; c->done = 1; f = 1; }
@@ -398,10 +396,11 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeC
         if (s_flag) return;
     }
 
+    __syncthreads();
     if (tid == 0) {
         if (!(c->lambda >= c->st.minLambda)) {                                                     // LS:1067-1072
-            T dmax = c->JJ[0];
-            for (int i = 1; i < n; ++i) { const T d = c->JJ[i * LARGE_NMAX + i]; if (t_abs(d) > t_abs(dmax)) dmax = d; }
+            T dmax = sA[0];
+            for (int i = 1; i < n; ++i) { const T d = sA[tri(i, i)]; if (t_abs(d) > t_abs(dmax)) dmax = d; }
             c->lambda = (T)(0.001 * (double)dmax);
             if (!(c->lambda >= c->st.minLambda)) c->lambda = (T)1;
         }
@@ -410,10 +409,9 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeC
     const T lambda = c->lambda;
     for (int k = tid; k < n; k += NT) { sq[k] = c->Jy[k]; sl[k] = c->l[k] - c->x[k]; su[k] = c->u[k] - c->x[k]; sx[k] = (T)0; }   // LS:1074-1077
     __syncthreads();
-    const T* JJ = c->JJ;
-    auto P = [&](int i, int j) -> T { const T v = JJ[i * LARGE_NMAX + j]; return i == j ? v + lambda : v; };   // LS:1078-1079
+    auto P = [&](int i, int j) -> T { const T v = sA[tri(i, j)]; return i == j ? v + lambda : v; };   // LS:1078-1079 (i >= j)
     unsigned iters = 0, solves = 0;
-    const int qs = cta_boxqp<T, NT>(c->st.qpSettings, n, P, sq, sl, su, sx, w, iters, solves);   // LS:1080
+    const int qs = cta_boxqp<T, NT, true>(c->st.qpSettings, n, P, sq, sl, su, sx, w, iters, solves);   // LS:1080
     __syncthreads();
     bool nan = false;                                                                              // LS:1087-1092
     for (int k = tid; k < n; k += NT) nan = nan || !(sx[k] <= sx[k]);
@@ -433,24 +431,30 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeC
         sx[k] = d; c->dX[k] = d;
     }
     __syncthreads();
+    bool differs = false;                                                                          // LS:1108-1110 (all threads)
+    for (int k = tid; k < n; k += NT) {
+        const T xk = c->x[k];
+        const T v = t_max(t_min(add_rn(sx[k], xk), c->u[k]), c->l[k]);
+        sq[k] = v;                                   // (sq is free now) trial point, published below if the step is taken
+        differs = differs || !((v == xk) && (signbit(v) == signbit(xk)));
+    }
+    const bool same = !cta_any<NT>(differs);
     if (tid == 0) {
         T nd = (T)0;                                                                               // LS:1099
         for (int k = 0; k < n; ++k) nd += sx[k] * sx[k];
         c->nd = nd;
+        int take = 0;
         if (!(sqrt_ni(nd) < c->st.maxStep)) { large_reject(c); c->skipRest = 1; }                  // LS:1101-1106
         else {
-            bool same = true;                                                                      // LS:1108-1110
-            for (int k = 0; k < n; ++k) {
-                const T xk = c->x[k];
-                const T v = t_max(t_min(add_rn(sx[k], xk), c->u[k]), c->l[k]);
-                c->xt[k] = v;
-                same = same && (v == xk) && (signbit(v) == signbit(xk));
-            }
+            take = 1;
             ++c->fCalls;                                                                           // LS:1112
             c->doEval = same ? 0 : 1;      // f(xt) == y bit for bit when xt == x: the evaluation is skipped, trial = residual
             if (same) c->rr = c->residual;
         }
+        s_flag = take;
     }
+    __syncthreads();
+    if (s_flag) for (int k = tid; k < n; k += NT) c->xt[k] = sq[k];
 }
 
 // after the (all-reduced) trial residual: LS:1117-1175, then the guards of the next pass
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
         // symv(Lower, 1, JJ, deltaX, 2, Jy) with the undamped JJ, then pred = -Jy . deltaX          LS:1141-1142
         for (int i = tid; i < n; i += NT) {
             T acc = (T)0;
-            for (int j = 0; j < n; ++j) acc += ((i >= j) ? c->JJ[i * LARGE_NMAX + j] : c->JJ[j * LARGE_NMAX + i]) * sdx[j];
+            for (int j = 0; j < n; ++j) acc += c->packed[trisym(i, j)] * sdx[j];
             const T v = acc + (T)2 * c->Jy[i];
             c->Jy[i] = v; sjy[i] = v;
         }

@@ -36,7 +36,7 @@ template <class T> struct LModelGaussMix {
         T acc = add_rn(p(n - 2), mul_rn(p(n - 1), t));
         for (int k = 0; k + 3 <= n - 2; k += 3) {
             const T z = mul_rn(sub_rn(t, p(k + 1)), p.a(k + 2));
-            acc = add_rn(acc, mul_rn(p(k), exp_repro(mul_rn((T)-0.5, mul_rn(z, z)))));
+            acc = add_rn(acc, mul_rn(p(k), exp_repro_tp(mul_rn((T)-0.5, mul_rn(z, z)))));
         }
         return sub_rn(acc, y);
     }
@@ -47,7 +47,7 @@ template <class T> struct LModelGaussMix {
             const T is = p.a(k + 2);
             const T z = mul_rn(sub_rn(t, p(k + 1)), is);
             const T zz = mul_rn(z, z);
-            const T e = exp_repro(mul_rn((T)-0.5, zz));
+            const T e = exp_repro_tp(mul_rn((T)-0.5, zz));
             const T ae = mul_rn(p(k), e);
             row[k] = e; row[k + 1] = mul_rn(mul_rn(ae, z), is); row[k + 2] = mul_rn(mul_rn(ae, zz), is);
         } else {
@@ -62,13 +62,13 @@ template <class T> struct LModelSumExp {
     __device__ static T aux_of(int, int, T) { return (T)0; }
     __device__ static T residual(const ParamView<T>& p, int n, T t, T y) {
         T acc = (T)0;
-        for (int k = 0; k + 1 < n; k += 2) acc = add_rn(acc, mul_rn(p(k), exp_repro(mul_rn(-p(k + 1), t))));
+        for (int k = 0; k + 1 < n; k += 2) acc = add_rn(acc, mul_rn(p(k), exp_repro_tp(mul_rn(-p(k + 1), t))));
         return sub_rn(acc, y);
     }
     __host__ __device__ static int jac_items(int n) { return n / 2; }
     __device__ static void jac_item(const ParamView<T>& p, int, int item, T t, T* row) {
         const int k = 2 * item;
-        const T e = exp_repro(mul_rn(-p(k + 1), t));
+        const T e = exp_repro_tp(mul_rn(-p(k + 1), t));
         row[k] = e; row[k + 1] = mul_rn(-mul_rn(p(k), t), e);
     }
 };
@@ -78,11 +78,11 @@ template <class T> struct LModelExpDecay3 {
     __host__ __device__ static bool valid_n(int n) { return n == 3; }
     __device__ static T aux_of(int, int, T) { return (T)0; }
     __device__ static T residual(const ParamView<T>& p, int, T t, T y) {
-        return sub_rn(add_rn(mul_rn(p(0), exp_repro(mul_rn(-p(1), t))), p(2)), y);
+        return sub_rn(add_rn(mul_rn(p(0), exp_repro_tp(mul_rn(-p(1), t))), p(2)), y);
     }
     __host__ __device__ static int jac_items(int) { return 1; }
     __device__ static void jac_item(const ParamView<T>& p, int, int, T t, T* row) {
-        const T e = exp_repro(mul_rn(-p(1), t));
+        const T e = exp_repro_tp(mul_rn(-p(1), t));
         row[0] = e; row[1] = mul_rn(-mul_rn(p(0), t), e); row[2] = (T)1;
     }
 };
@@ -91,10 +91,10 @@ template <class T> struct LModelExpDecay3 {
 template <class T> struct LModelExpDecay2 {
     __host__ __device__ static bool valid_n(int n) { return n == 2; }
     __device__ static T aux_of(int, int, T) { return (T)0; }
-    __device__ static T residual(const ParamView<T>& p, int, T t, T y) { return sub_rn(mul_rn(p(0), exp_repro(mul_rn(-t, p(1)))), y); }
+    __device__ static T residual(const ParamView<T>& p, int, T t, T y) { return sub_rn(mul_rn(p(0), exp_repro_tp(mul_rn(-t, p(1)))), y); }
     __host__ __device__ static int jac_items(int) { return 1; }
     __device__ static void jac_item(const ParamView<T>& p, int, int, T t, T* row) {
-        const T e = exp_repro(mul_rn(-t, p(1)));
+        const T e = exp_repro_tp(mul_rn(-t, p(1)));
         row[0] = e; row[1] = mul_rn(-mul_rn(p(0), t), e);
     }
 };
@@ -104,11 +104,11 @@ template <class T> struct LModelExpTau3 {
     __host__ __device__ static bool valid_n(int n) { return n == 3; }
     __device__ static T aux_of(int, int, T) { return (T)0; }
     __device__ static T residual(const ParamView<T>& p, int, T t, T y) {
-        return sub_rn(add_rn(mul_rn(p(0), exp_repro(div_ni(-t, p(1)))), p(2)), y);
+        return sub_rn(add_rn(mul_rn(p(0), exp_repro_tp(div_ni(-t, p(1)))), p(2)), y);
     }
     __host__ __device__ static int jac_items(int) { return 1; }
     __device__ static void jac_item(const ParamView<T>& p, int, int, T t, T* row) {
-        const T e = exp_repro(div_ni(-t, p(1)));
+        const T e = exp_repro_tp(div_ni(-t, p(1)));
         row[0] = e; row[1] = div_ni(mul_rn(mul_rn(p(0), e), t), mul_rn(p(1), p(1))); row[2] = (T)1;
     }
 };
@@ -119,14 +119,14 @@ template <class T> struct LModelGauss4 {
     __device__ static T aux_of(int k, int, T v) { return k == 2 ? rcp_ni(v) : (T)0; }
     __device__ static T residual(const ParamView<T>& p, int, T t, T y) {
         const T z = mul_rn(sub_rn(t, p(1)), p.a(2));
-        return sub_rn(add_rn(mul_rn(p(0), exp_repro(mul_rn((T)-0.5, mul_rn(z, z)))), p(3)), y);
+        return sub_rn(add_rn(mul_rn(p(0), exp_repro_tp(mul_rn((T)-0.5, mul_rn(z, z)))), p(3)), y);
     }
     __host__ __device__ static int jac_items(int) { return 1; }
     __device__ static void jac_item(const ParamView<T>& p, int, int, T t, T* row) {
         const T is = p.a(2);
         const T z = mul_rn(sub_rn(t, p(1)), is);
         const T zz = mul_rn(z, z);
-        const T e = exp_repro(mul_rn((T)-0.5, zz));
+        const T e = exp_repro_tp(mul_rn((T)-0.5, zz));
         const T ae = mul_rn(p(0), e);
         row[0] = e; row[1] = mul_rn(mul_rn(ae, z), is); row[2] = mul_rn(mul_rn(ae, zz), is); row[3] = (T)1;
     }
