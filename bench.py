@@ -40,7 +40,8 @@ sys.path.insert(0, ROOT)
 M, N = 64, 4
 C_F, C_G = 8, 6          # model flops per row for f, and for the analytic Jacobian given f's intermediates
 WORKLOAD = ("configs[1]: batched independent 4-parameter Gaussian-peak fits, m=64 samples each, double, box bounds, "
-            "analytic Jacobian, reference default settings, one warp per problem")
+            "analytic Jacobian, reference default settings (BASELINE names it 'one warp per problem'; at this batch size the "
+            "library runs one THREAD per problem, see roofline.kernel)")
 
 
 def algorithmic_flops(stats, m=M, n=N):
