@@ -99,6 +99,6 @@ __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j
 __host__ __device__ constexpr int trisym(int i, int j) { return i >= j ? tri(i, j) : tri(j, i); }
 
 // Launch accounting (mir_b200_kernel_launches)
-void count_launch(unsigned n = 1);
+void count_launch(long long n = 1);
 
 }  // namespace mirb200

@@ -68,12 +68,12 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate");
     CK(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking), "cudaStreamCreate");
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
-    CK(cudaMallocHost((void**)&h_wm, sizeof(unsigned int) * (nchunks + 1)), "cudaMallocHost(watermarks)");
+    h_wm = static_cast<unsigned int*>(pinned_scratch(sizeof(unsigned int) * (nchunks + 1)));
+    if (!h_wm && rc == MIR_B200_OK) { set_error("mir_optim_b200: cannot allocate pinned host scratch"); rc = MIR_B200_ECUDA; }
     auto cleanup = [&]() {
         if (cs) cudaStreamDestroy(cs);
         if (ps) cudaStreamDestroy(ps);
         if (ev) cudaEventDestroy(ev);
-        if (h_wm) cudaFreeHost(h_wm);
     };
     if (rc != MIR_B200_OK) { cleanup(); return rc; }
 

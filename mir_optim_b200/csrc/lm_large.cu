@@ -4,7 +4,10 @@
 //   mir_b200_syrk_lower_dev_d                 the J^T J kernel alone (roofline measurements)
 // Kernels: lm_large.cuh, syrk_dmma.cuh.  No CPU fallback anywhere: without a device every entry
 // point reports an error (legacy entries: status numericError + mir_b200_last_error()).
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -197,6 +200,24 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
     if (rc) return rc;
     if (comm && (rc = nccl_available())) return rc;
 
+    // All work runs on an internal stream ordered after the caller's stream: the pass loop is replayed as a CUDA graph,
+    // and the legacy default stream (what a caller may well hand in) cannot be captured.  The call is blocking anyway.
+    struct WorkStream {
+        cudaStream_t s = nullptr; cudaEvent_t e = nullptr;
+        ~WorkStream() { if (e) cudaEventDestroy(e); if (s) cudaStreamDestroy(s); }
+    } work;
+    MIRB200_CUDA(cudaStreamCreateWithFlags(&work.s, cudaStreamNonBlocking));
+    MIRB200_CUDA(cudaEventCreateWithFlags(&work.e, cudaEventDisableTiming));
+    MIRB200_CUDA(cudaEventRecord(work.e, stream));
+    MIRB200_CUDA(cudaStreamWaitEvent(work.s, work.e, 0));
+    stream = work.s;
+
+    // double: the Broyden update runs inside the SYRK ring (syrk_dmma.cuh); MIRB200_NO_BROYDEN_FUSE=1 keeps the separate kernel (experiments)
+    static const bool noFuse = [] { const char* e = std::getenv("MIRB200_NO_BROYDEN_FUSE"); return e && *e == '1'; }();
+    const bool fuseBroyden = kDouble && !noFuse;
+    static const bool trace = [] { const char* e = std::getenv("MIRB200_TRACE"); return e && *e == '1'; }();
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto TR = [&](const char* what) { if (trace) { cudaStreamSynchronize(stream); fprintf(stderr, "[trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count()); } };
     const int ldj = (n + 1) & ~1;
     const long long rowsPad = (rows + SYRK_KT - 1) / SYRK_KT * SYRK_KT;
     const int sms = sm_count();
@@ -229,6 +250,7 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
     if (rowsPad > rows) MIRB200_CUDA(cudaMemsetAsync(d_J + (size_t)rows * ldj, 0, sizeof(T) * (size_t)(rowsPad - rows) * ldj, stream));
     if (ldj > n && cb) MIRB200_CUDA(cudaMemsetAsync(d_J, 0, sizeof(T) * (size_t)rows * ldj, stream));   // pad column (host J has pitch n)
 
+    TR("alloc");
     // ---- control block ----
     std::unique_ptr<Ctl> h(new Ctl);
     std::memset(h.get(), 0, sizeof(Ctl));
@@ -280,7 +302,7 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
         if (!cb) {
             auto jk = fdJacobian ? K.jacfd : K.jac;
             jk<<<gridJac, 256, jacSmem, stream>>>(ja); count_launch();
-            large_broyden_kernel<T, true><<<gridBro, 256, 0, stream>>>(ja); count_launch();
+            if (!fuseBroyden) { large_broyden_kernel<T, true><<<gridBro, 256, 0, stream>>>(ja); count_launch(); }   // else: fused into the SYRK ring
         } else {
             Mail m; if (int r = fetch(m, false)) return r;
             if (!m.done && m.jacMode == JAC_FRESH) {
@@ -295,10 +317,12 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
                 MIRB200_CUDA(cudaMemcpy2DAsync(d_J, sizeof(T) * ldj, hJ.data(), sizeof(T) * n, sizeof(T) * n, (size_t)rows, cudaMemcpyHostToDevice, stream));
             }
             large_broyden_kernel<T, false><<<gridBro, 256, 0, stream>>>(ja); count_launch();
-            large_broyden_kernel<T, true><<<gridBro, 256, 0, stream>>>(ja); count_launch();
+            if (!fuseBroyden) { large_broyden_kernel<T, true><<<gridBro, 256, 0, stream>>>(ja); count_launch(); }
         }
         if (kDouble) {
-            SyrkArgs sa{(const double*)d_J, rowsPad / SYRK_KT, ldj, (n + 7) / 8, (double*)d_part, &d_ctl->jacMode, &d_ctl->done};
+            SyrkBroyden sb{fuseBroyden ? 1 : 0, (double*)d_J, (const double*)d_b0, (const double*)d_b1, &d_ctl->ysel, (const double*)d_ctl->dX,
+                           (const double*)&d_ctl->deltaX_dot, rows, (double*)d_partJy, &d_ctl->ticket[1], (double*)d_ctl->packed + np, n};
+            SyrkArgs sa{(const double*)d_J, rowsPad / SYRK_KT, ldj, (n + 7) / 8, (double*)d_part, &d_ctl->jacMode, &d_ctl->done, sb};
             syrk_dmma_kernel<<<gridSyrk, SYRK_THREADS, SYRK_SMEM_BYTES, stream>>>(sa); count_launch();
             syrk_reduce_kernel<<<(np + 255) / 256, 256, 0, stream>>>((const double*)d_part, (int)gridSyrk, n, (double*)d_ctl->packed, &d_ctl->jacMode, &d_ctl->done);
             count_launch();
@@ -320,38 +344,69 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
         return check_cuda(cudaGetLastError(), "large_ctl_post_kernel");
     };
 
+    TR("setup");
     // ---- initial residual, LS:953-956 ----
     if ((rc = step_eval())) return rc;
     if ((rc = step_post())) return rc;
 
+    TR("initial residual");
     // ---- passes: enqueued in chunks, `done` polled one chunk behind ----
-    int* h_done = nullptr;
-    MIRB200_CUDA(cudaMallocHost((void**)&h_done, 2 * sizeof(int)));
-    struct FreeHost { int* p; ~FreeHost() { cudaFreeHost(p); } } fh{h_done};
+    int* h_done = static_cast<int*>(pinned_scratch(2 * sizeof(int)));
+    if (!h_done) { set_error("mir_optim_b200: cannot allocate pinned host scratch"); return MIR_B200_ECUDA; }
     h_done[0] = h_done[1] = 0;
     cudaEvent_t ev[2];
     MIRB200_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     MIRB200_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     struct FreeEv { cudaEvent_t* e; ~FreeEv() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } fe{ev};
     const int chunk = cb ? 1 : 4;
+    auto enqueue_chunk = [&]() -> int {
+        for (int k = 0; k < chunk; ++k) {
+            if (int r = step_jacobian()) return r;
+            if (int r = step_mid()) return r;
+            if (int r = step_eval()) return r;
+            if (int r = step_post()) return r;
+        }
+        // `done` only ever goes 0 -> 1, so one host slot serves every chunk
+        return check_cuda(cudaMemcpyAsync(&h_done[0], (char*)d_ctl + offsetof(Ctl, done), sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H done");
+    };
+    // Every kernel of a pass takes its arguments from the device-resident control block, so a chunk of passes is the
+    // same ~40 launches (+ all-reduces) every time: captured once and replayed as a CUDA graph, the host issues one
+    // call per chunk and its scheduling jitter no longer reaches the GPU (measured on shared B200 hosts: the same solve
+    // took 0.17 - 0.99 s with direct launches).  Host callbacks need the host between kernels: direct launches.
+    struct GraphHolder {
+        cudaGraph_t g = nullptr; cudaGraphExec_t x = nullptr;
+        ~GraphHolder() { if (x) cudaGraphExecDestroy(x); if (g) cudaGraphDestroy(g); }
+    } graph;
+    static const bool noGraph = [] { const char* e = std::getenv("MIRB200_NO_GRAPH"); return e && *e == '1'; }();
+    unsigned launchesPerChunk = 0;
+    if (!cb && !noGraph) {
+        const unsigned long long l0 = mir_b200_kernel_launches();
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rcap = enqueue_chunk();
+            const cudaError_t ec = cudaStreamEndCapture(stream, &graph.g);
+            if (rcap != MIR_B200_OK || ec != cudaSuccess || cudaGraphInstantiate(&graph.x, graph.g, 0) != cudaSuccess) {
+                cudaGetLastError(); clear_error();
+                if (graph.x) { cudaGraphExecDestroy(graph.x); graph.x = nullptr; }
+            }
+        } else cudaGetLastError();
+        launchesPerChunk = (unsigned)(mir_b200_kernel_launches() - l0);
+        count_launch(-(long long)launchesPerChunk);     // the capture pass launched nothing
+    }
     bool finished = false;
     for (unsigned long long c = 0; !finished; ++c) {
-        for (int k = 0; k < chunk; ++k) {
-            if ((rc = step_jacobian())) return rc;
-            if ((rc = step_mid())) return rc;
-            if ((rc = step_eval())) return rc;
-            if ((rc = step_post())) return rc;
-        }
+        if (graph.x) { MIRB200_CUDA(cudaGraphLaunch(graph.x, stream)); count_launch(launchesPerChunk); }
+        else if ((rc = enqueue_chunk())) return rc;
         const int slot = (int)(c & 1);
-        MIRB200_CUDA(cudaMemcpyAsync(&h_done[slot], (char*)d_ctl + offsetof(Ctl, done), sizeof(int), cudaMemcpyDeviceToHost, stream));
         MIRB200_CUDA(cudaEventRecord(ev[slot], stream));
-        if (cb) { MIRB200_CUDA(cudaEventSynchronize(ev[slot])); finished = h_done[slot] != 0; }
-        else if (c >= 1) { MIRB200_CUDA(cudaEventSynchronize(ev[slot ^ 1])); finished = h_done[slot ^ 1] != 0; }
+        if (cb) { MIRB200_CUDA(cudaEventSynchronize(ev[slot])); finished = h_done[0] != 0; }
+        else if (c >= 1) { MIRB200_CUDA(cudaEventSynchronize(ev[slot ^ 1])); finished = h_done[0] != 0; }
     }
 
+    TR("passes");
     // ---- results ----
     MIRB200_CUDA(cudaMemcpyAsync(h.get(), d_ctl, offsetof(Ctl, JJ), cudaMemcpyDeviceToHost, stream));
     MIRB200_CUDA(cudaStreamSynchronize(stream));
+    TR("results");
     for (int i = 0; i < n; ++i) x[i] = h->x[i];
     result->status = h->status; result->iterations = h->iterations; result->fCalls = h->fCalls; result->gCalls = h->gCalls;
     result->residual = h->residual; result->lambda = h->lambda;
@@ -484,7 +539,7 @@ int mir_b200_syrk_lower_dev_d(const double* J, size_t rows, size_t n, size_t ldj
     const int hf[2] = {1, 0};
     MIRB200_CUDA(cudaMemcpyAsync(flags, hf, sizeof hf, cudaMemcpyHostToDevice, stream));
     MIRB200_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM_BYTES));
-    SyrkArgs sa{J, tiles, (int)ldj, (int)((n + 7) / 8), part, flags, flags + 1};
+    SyrkArgs sa{J, tiles, (int)ldj, (int)((n + 7) / 8), part, flags, flags + 1, SyrkBroyden{}};
     syrk_dmma_kernel<<<grid, SYRK_THREADS, SYRK_SMEM_BYTES, stream>>>(sa); count_launch();
     const int np = (int)(n * (n + 1) / 2);
     syrk_reduce_kernel<<<(np + 255) / 256, 256, 0, stream>>>(part, (int)grid, (int)n, packed, flags, flags + 1); count_launch();

@@ -11,7 +11,7 @@ static std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const std::string& msg) { g_error = msg; }
 void clear_error() { g_error.clear(); }
-void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_launch(long long n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int check_cuda(cudaError_t e, const char* what)
 {
@@ -58,6 +58,22 @@ int require_device(int device)
     }
     keep_pool_cached();
     return MIR_B200_OK;
+}
+
+// Small pinned host scratch, one grow-only buffer per host thread, never freed before process exit:
+// cudaMallocHost / cudaFreeHost synchronise the context and go through the OS, and were measured to add anything from
+// 1 ms to several hundred ms to a solve on busy hosts when done per call.
+void* pinned_scratch(size_t bytes)
+{
+    static thread_local void* buf = nullptr;
+    static thread_local size_t cap = 0;
+    if (bytes <= cap) return buf;
+    void* nb = nullptr;
+    const size_t want = bytes < 4096 ? 4096 : bytes;
+    if (cudaMallocHost(&nb, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // (the previous, smaller buffer is intentionally leaked: an in-flight copy may still target it)
+    buf = nb; cap = want;
+    return buf;
 }
 
 int sm_count()

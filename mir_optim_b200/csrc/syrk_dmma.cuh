@@ -38,14 +38,37 @@ constexpr int SYRK_THREADS = (SYRK_CONSUMERS + 1) * 32;
 constexpr size_t SYRK_STAGE_BYTES = (size_t)SYRK_KT * SYRK_PITCH;
 constexpr size_t SYRK_SMEM_BYTES = SYRK_STAGES * SYRK_STAGE_BYTES + 2 * SYRK_STAGES * sizeof(unsigned long long) + 128;
 
+// Optional fused Broyden update (least_squares.d:999-1006 + the gemv at :1052): when enabled and *gate == 1, every tile
+// is updated IN the shared-memory ring before the DMMAs read it --
+//     v = ((f_old - f_new) + J_row . dX) * (-1 / |dX|^2),   J_row += v dX',   J'y += J_row * f_new
+// -- written back to HBM from registers, and J'y leaves through per-CTA partials added in CTA order by the last CTA.
+// The separate Broyden kernel streamed J twice (read + write, 8.2 GB, 1.40 ms HBM-bound at 4M x 128) before this kernel
+// read it a third time; fused, the update hides under the tensor pipe.  Row arithmetic is the standalone kernel's,
+// operation for operation (same lane layout and shuffle tree), so J comes out bit-identical.
+struct SyrkBroyden {
+    int           enabled;
+    double*       J;            // writable alias of SyrkArgs::J
+    const double* buf0;         // y / mBuffer pair, selected by *ysel as in lm_large.cuh
+    const double* buf1;
+    const int*    ysel;
+    const double* dX;           // accepted step, n values
+    const double* deltaX_dot;   // |dX|^2
+    long long     rows;         // valid rows of this rank (<= tiles * KT)
+    double*       partJy;       // gridDim.x * 128
+    unsigned*     ticket;       // last-CTA ticket (zero on entry, reset on exit)
+    double*       outJy;        // n values
+    int           n;
+};
+
 struct SyrkArgs {
     const double* J;        // rowsPadded x ldj, row-major; rows >= rows are zero (the engine pads to a multiple of KT)
     long long     tiles;    // rowsPadded / KT
     int           ldj;      // even, <= 128
     int           nblk;     // ceil(n / 8)
     double*       partial;  // gridDim.x images of 128 x 128 doubles
-    const int*    gate;     // device flag: 0 => nothing to do this pass (J unchanged)
+    const int*    gate;     // device flag: 0 => nothing to do this pass (J unchanged); 1 = Broyden pass, 2 = fresh Jacobian
     const int*    done;     // device flag: solve finished
+    SyrkBroyden   bro;      // bro.enabled == 0: plain J^T J whatever the gate says
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -87,68 +110,61 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// Consumer warp W: block-rows A = W and B = 15 - W of the lower triangle.
+// Consumer warp W owns block-rows A = W and B = 15 - W of the lower triangle: W + 1 and 16 - W blocks = 17 accumulator
+// pairs for every W, kept in one uniform array so that the per-tile loop (and the fused Broyden update in it) exists
+// ONCE in the kernel and only the DMMA block of a tile is specialised per warp -- eight fully specialised consumer
+// loops plus an inlined update overflowed the instruction cache (ncu: stall_no_instruction 8.4, tensor pipe 37 %).
 template <int W>
-__device__ __forceinline__ void syrk_consume(const SyrkArgs& a, const unsigned char* stages, unsigned long long* full,
-                                             unsigned long long* empty, long long tile0, long long tile1, int lane)
+__device__ __forceinline__ void syrk_mma_tile(double (&c)[17][2], const double* tile, int nblk)
 {
     constexpr int RA = W, RB = 15 - W;          // RA < RB
     constexpr int NF = RB + 1;                  // fragments per k-step: block-columns 0..RB
-    double ca[RA + 1][2], cb[RB + 1][2];
-#pragma unroll
-    for (int j = 0; j <= RA; ++j) { ca[j][0] = 0.0; ca[j][1] = 0.0; }
-#pragma unroll
-    for (int j = 0; j <= RB; ++j) { cb[j][0] = 0.0; cb[j][1] = 0.0; }
-    const int nblk = a.nblk;
-    const int fragOff = (lane & 3) * SYRK_PITCH_D + (lane >> 2);
-
-    for (long long it = tile0; it < tile1; ++it) {
-        const long long k = it - tile0;
-        const int s = (int)(k % SYRK_STAGES);
-        mbar_wait(&full[s], (unsigned)((k / SYRK_STAGES) & 1));
-        const double* tile = reinterpret_cast<const double*>(stages + (size_t)s * SYRK_STAGE_BYTES) + fragOff;
 #pragma unroll 2
-        for (int ks = 0; ks < SYRK_KT / 4; ++ks) {
-            const double* row = tile + ks * 4 * SYRK_PITCH_D;
-            double f[NF];
-            if (nblk == 16) {
+    for (int ks = 0; ks < SYRK_KT / 4; ++ks) {
+        const double* row = tile + ks * 4 * SYRK_PITCH_D;
+        double f[NF];
+        if (nblk == 16) {
 #pragma unroll
-                for (int j = 0; j < NF; ++j) f[j] = row[8 * j];
+            for (int j = 0; j < NF; ++j) f[j] = row[8 * j];
 #pragma unroll
-                for (int j = 0; j <= RA; ++j) dmma884(ca[j], f[RA], f[j]);
+            for (int j = 0; j <= RA; ++j) dmma884(c[j], f[RA], f[j]);
 #pragma unroll
-                for (int j = 0; j <= RB; ++j) dmma884(cb[j], f[RB], f[j]);
-            } else {
+            for (int j = 0; j <= RB; ++j) dmma884(c[RA + 1 + j], f[RB], f[j]);
+        } else {
 #pragma unroll
-                for (int j = 0; j < NF; ++j) f[j] = (j < nblk) ? row[8 * j] : 0.0;
-                if (RA < nblk) {
+            for (int j = 0; j < NF; ++j) f[j] = (j < nblk) ? row[8 * j] : 0.0;
+            if (RA < nblk) {
 #pragma unroll
-                    for (int j = 0; j <= RA; ++j) dmma884(ca[j], f[RA], f[j]);
-                }
-                if (RB < nblk) {
+                for (int j = 0; j <= RA; ++j) dmma884(c[j], f[RA], f[j]);
+            }
+            if (RB < nblk) {
 #pragma unroll
-                    for (int j = 0; j <= RB; ++j) if (j < nblk) dmma884(cb[j], f[RB], f[j]);
-                }
+                for (int j = 0; j <= RB; ++j) if (j < nblk) dmma884(c[RA + 1 + j], f[RB], f[j]);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
     }
+}
 
-    // epilogue: C fragment of m8n8k4 = row lane/4, columns 2*(lane%4) + {0,1}
-    double* out = a.partial + (size_t)blockIdx.x * (SYRK_NPAD * SYRK_NPAD);
-    const int r = lane >> 2, c = (lane & 3) * 2;
+// epilogue: C fragment of m8n8k4 = row lane/4, columns 2*(lane%4) + {0,1}
+template <int W>
+__device__ __forceinline__ void syrk_store_blocks(const double (&c)[17][2], double* out, int lane)
+{
+    constexpr int RA = W, RB = 15 - W;
+    const int r = lane >> 2, col = (lane & 3) * 2;
 #pragma unroll
     for (int j = 0; j <= RA; ++j)
-        *reinterpret_cast<double2*>(out + (size_t)(8 * RA + r) * SYRK_NPAD + 8 * j + c) = make_double2(ca[j][0], ca[j][1]);
+        *reinterpret_cast<double2*>(out + (size_t)(8 * RA + r) * SYRK_NPAD + 8 * j + col) = make_double2(c[j][0], c[j][1]);
 #pragma unroll
     for (int j = 0; j <= RB; ++j)
-        *reinterpret_cast<double2*>(out + (size_t)(8 * RB + r) * SYRK_NPAD + 8 * j + c) = make_double2(cb[j][0], cb[j][1]);
+        *reinterpret_cast<double2*>(out + (size_t)(8 * RB + r) * SYRK_NPAD + 8 * j + col) = make_double2(c[RA + 1 + j][0], c[RA + 1 + j][1]);
 }
 
 __global__ void __launch_bounds__(SYRK_THREADS, 1) syrk_dmma_kernel(const SyrkArgs a)
 {
     if (*a.done || *a.gate == 0) return;
+    const bool fuse = a.bro.enabled && *a.gate == 1;
+    __shared__ double s_jy[SYRK_CONSUMERS * SYRK_NPAD];
+    __shared__ bool s_last;
     extern __shared__ __align__(128) unsigned char syrk_smem[];
     unsigned char* stages = syrk_smem;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(syrk_smem + SYRK_STAGES * SYRK_STAGE_BYTES);
@@ -183,16 +199,119 @@ __global__ void __launch_bounds__(SYRK_THREADS, 1) syrk_dmma_kernel(const SyrkAr
             tma_bulk_g2s(stages + (size_t)s * SYRK_STAGE_BYTES + (size_t)lane * SYRK_PITCH, src, rowBytes, &full[s]);
         }
     } else {
-        switch (warp) {
-            case 0: syrk_consume<0>(a, stages, full, empty, tile0, tile1, lane); break;
-            case 1: syrk_consume<1>(a, stages, full, empty, tile0, tile1, lane); break;
-            case 2: syrk_consume<2>(a, stages, full, empty, tile0, tile1, lane); break;
-            case 3: syrk_consume<3>(a, stages, full, empty, tile0, tile1, lane); break;
-            case 4: syrk_consume<4>(a, stages, full, empty, tile0, tile1, lane); break;
-            case 5: syrk_consume<5>(a, stages, full, empty, tile0, tile1, lane); break;
-            case 6: syrk_consume<6>(a, stages, full, empty, tile0, tile1, lane); break;
-            default: syrk_consume<7>(a, stages, full, empty, tile0, tile1, lane); break;
+        double c[17][2];
+#pragma unroll
+        for (int j = 0; j < 17; ++j) { c[j][0] = 0.0; c[j][1] = 0.0; }
+        const int nblk = a.nblk;
+        const int fragOff = (lane & 3) * SYRK_PITCH_D + (lane >> 2);
+
+        // fused Broyden state: this warp updates rows 4*warp .. 4*warp+3 of every tile; lane owns columns lane + 32 q
+        double dx[4] = {0.0, 0.0, 0.0, 0.0}, jy[4] = {0.0, 0.0, 0.0, 0.0};
+        double negd = 0.0, pf = 0.0;
+        const double* yv = nullptr; const double* mbv = nullptr;
+        auto fetch_pf = [&](long long tileIdx) -> double {       // lanes 0-3: f_new of my 4 rows, lanes 4-7: f_old
+            const long long row = tileIdx * SYRK_KT + 4 * warp + (lane & 3);
+            if (lane < 8 && tileIdx < tile1 && row < a.bro.rows) return (lane < 4 ? yv : mbv)[row];
+            return 0.0;
+        };
+        if (fuse) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int col = lane + 32 * q; dx[q] = col < a.bro.n ? a.bro.dX[col] : 0.0; }
+            negd = -(1.0 / *a.bro.deltaX_dot);                                                   // LS:1001
+            const int ys = *a.bro.ysel;
+            yv = ys ? a.bro.buf1 : a.bro.buf0; mbv = ys ? a.bro.buf0 : a.bro.buf1;
+            pf = fetch_pf(tile0);
         }
+
+        for (long long it = tile0; it < tile1; ++it) {
+            const long long k = it - tile0;
+            const int s = (int)(k % SYRK_STAGES);
+            double pfNext = 0.0;
+            if (fuse) pfNext = fetch_pf(it + 1);                  // next tile's residuals: in flight during this tile
+            mbar_wait(&full[s], (unsigned)((k / SYRK_STAGES) & 1));
+            if (fuse) {
+                double* trow = reinterpret_cast<double*>(stages + (size_t)s * SYRK_STAGE_BYTES) + (size_t)(4 * warp) * SYRK_PITCH_D;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const long long row = it * SYRK_KT + 4 * warp + r;
+                    double jv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) jv[q] = trow[r * SYRK_PITCH_D + lane + 32 * q];
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc += jv[q] * dx[q];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                    const double yr = __shfl_sync(0xffffffffu, pf, r), mbr = __shfl_sync(0xffffffffu, pf, 4 + r);
+                    const double v = (row < a.bro.rows) ? ((mbr - yr) + acc) * negd : 0.0;       // LS:1003-1005 (padding rows stay zero)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = lane + 32 * q;
+                        jv[q] += v * dx[q];                                                      // LS:1006
+                        trow[r * SYRK_PITCH_D + col] = jv[q];
+                        if (col < a.ldj && row < a.bro.rows) a.bro.J[(size_t)row * a.ldj + col] = jv[q];
+                        jy[q] += jv[q] * yr;                                                     // LS:1052
+                    }
+                }
+                pf = pfNext;
+                asm volatile("bar.sync 1, %0;" ::"n"(SYRK_CONSUMERS * 32) : "memory");          // all 32 rows updated before any fragment load
+            }
+            const double* tile = reinterpret_cast<const double*>(stages + (size_t)s * SYRK_STAGE_BYTES) + fragOff;
+            switch (warp) {
+                case 0: syrk_mma_tile<0>(c, tile, nblk); break;
+                case 1: syrk_mma_tile<1>(c, tile, nblk); break;
+                case 2: syrk_mma_tile<2>(c, tile, nblk); break;
+                case 3: syrk_mma_tile<3>(c, tile, nblk); break;
+                case 4: syrk_mma_tile<4>(c, tile, nblk); break;
+                case 5: syrk_mma_tile<5>(c, tile, nblk); break;
+                case 6: syrk_mma_tile<6>(c, tile, nblk); break;
+                default: syrk_mma_tile<7>(c, tile, nblk); break;
+            }
+            if (fuse) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile writes before the next TMA fill
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        double* out = a.partial + (size_t)blockIdx.x * (SYRK_NPAD * SYRK_NPAD);
+        switch (warp) {
+            case 0: syrk_store_blocks<0>(c, out, lane); break;
+            case 1: syrk_store_blocks<1>(c, out, lane); break;
+            case 2: syrk_store_blocks<2>(c, out, lane); break;
+            case 3: syrk_store_blocks<3>(c, out, lane); break;
+            case 4: syrk_store_blocks<4>(c, out, lane); break;
+            case 5: syrk_store_blocks<5>(c, out, lane); break;
+            case 6: syrk_store_blocks<6>(c, out, lane); break;
+            default: syrk_store_blocks<7>(c, out, lane); break;
+        }
+        if (fuse) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s_jy[warp * SYRK_NPAD + lane + 32 * q] = jy[q];
+        }
+    }
+    if (!fuse) return;
+
+    // J'y: warps in fixed order -> this CTA's partial -> the last CTA adds the partials in CTA order
+    __syncthreads();
+    if (tid < SYRK_NPAD) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < SYRK_CONSUMERS; ++w) sum += s_jy[w * SYRK_NPAD + tid];
+        a.bro.partJy[(size_t)blockIdx.x * SYRK_NPAD + tid] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.bro.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int col = tid; col < a.bro.n; col += SYRK_THREADS) {
+            double s0 = 0.0, s1 = 0.0;
+            int b = 0;
+            for (; b + 2 <= (int)gridDim.x; b += 2) { s0 += a.bro.partJy[(size_t)b * SYRK_NPAD + col]; s1 += a.bro.partJy[(size_t)(b + 1) * SYRK_NPAD + col]; }
+            if (b < (int)gridDim.x) s0 += a.bro.partJy[(size_t)b * SYRK_NPAD + col];
+            a.bro.outJy[col] = s0 + s1;
+        }
+        if (tid == 0) *a.bro.ticket = 0;
     }
 }
 

@@ -107,14 +107,20 @@ def test_c4_sharded_entry_single_gpu_with_bounds(eng, oracle_lib):
 
 
 def test_large_path_tail_fast_forward_is_bit_identical(eng):
-    """Same check as the batched one, on the single-problem path (large_begin_pass)."""
+    """Same check as the batched one, on the single-problem path (large_begin_pass).  Which exit a noisy fit takes hangs
+    on rounding, so several data sets are run: every one must be bit-identical with and without the
+    shortcut, and at least one must leave through the lambda-overflow tail (furtherImprovement) that the shortcut replays."""
     from mir_optim_b200 import workloads
-    wl = workloads.c4_gaussmix(m=20000, K=6, noise=1e-3)
     s = eng.settings()
-    got = []
-    for shortcut in (True, False):
-        x = wl.x0[0].copy()
-        r = eng.optimize_device_model(s, wl.model, x, wl.l, wl.u, t=wl.t, y=wl.y.reshape(-1), tail_shortcut=shortcut)
-        got.append((x.tobytes(), r.status, r.iterations, r.fCalls, r.gCalls, r.residual, r.lambda_))
-    assert got[0] == got[1]
-    assert got[0][1] == 0          # furtherImprovement through the lambda-overflow exit
+    statuses = []
+    for seed in (4, 5, 6, 7, 8, 9):
+        wl = workloads.c4_gaussmix(m=20000, K=6, noise=1e-3, seed=seed)
+        got = []
+        for shortcut in (True, False):
+            x = wl.x0[0].copy()
+            r = eng.optimize_device_model(s, wl.model, x, wl.l, wl.u, t=wl.t, y=wl.y.reshape(-1), tail_shortcut=shortcut)
+            got.append((x.tobytes(), r.status, r.iterations, r.fCalls, r.gCalls, r.residual, r.lambda_))
+        assert got[0] == got[1], seed
+        assert got[0][1] >= 0, seed
+        statuses.append(got[0][1])
+    assert 0 in statuses, statuses          # furtherImprovement through the lambda-overflow exit
