@@ -379,6 +379,9 @@ def main():
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     t_h, y_h, x0_h, l_h, u_h = pin(wl.t), pin(wl.y), pin(wl.x0), pin(wl.l), pin(wl.u)
     x_h = torch.empty_like(x0_h).pin_memory()
+    from mir_optim_b200.engine import RESULT_DTYPES
+    res_pin = torch.empty(B * 32, dtype=torch.uint8).pin_memory()              # the Result PODs land in pinned memory too
+    res_view = res_pin.numpy().view(RESULT_DTYPES[np.dtype(np.float64)])
     e2e_t = 0.0
     res_e2e = None
     for i in range(2 + args.steps):
@@ -386,7 +389,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         res_e2e, _ = eng.optimize_batched(settings, wl.model, x_h.numpy(), l_h.numpy(), u_h.numpy(), t=t_h.numpy(), y=y_h.numpy(),
-                                          device=local_rank)
+                                          device=local_rank, results=res_view)
         dt = time.perf_counter() - t0
         if i >= 2:
             e2e_t += max_over_ranks(dt)

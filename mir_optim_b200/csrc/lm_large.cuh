@@ -52,7 +52,8 @@ template <class T> struct LargeCtl {
     unsigned long long passes, accepted, fresh, broyden, evals, qpSolves, qpIters;
     T rr;                        // ||f(trial)||^2 (all-reduced in place)
     T x[LARGE_NMAX], xt[LARGE_NMAX], l[LARGE_NMAX], u[LARGE_NMAX], dX[LARGE_NMAX], Jy[LARGE_NMAX];
-    T JJ[LARGE_NMAX * LARGE_NMAX];                   // lower triangle, row-major, undamped
+    T JJ[LARGE_NMAX * LARGE_NMAX];                   // PACKED lower triangle (tri(i,j)), undamped: the copy of `packed` taken right after
+                                                     // its all-reduce (the host all-reduces `packed` on every pass, also when J did not change)
     T packed[LARGE_NP_MAX + LARGE_NMAX];             // [lower(J^T J) by rows | J^T y]  (all-reduced in place)
 };
 
@@ -377,7 +378,11 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeC
     __shared__ int s_flag;
     const int np = n * (n + 1) / 2;
 
-    for (int e = tid; e < np; e += NT) sA[e] = c->packed[e];
+    if (c->jacMode != JAC_NONE) {
+        for (int e = tid; e < np; e += NT) { const T v = c->packed[e]; c->JJ[e] = v; sA[e] = v; }
+    } else {
+        for (int e = tid; e < np; e += NT) sA[e] = c->JJ[e];
+    }
     if (c->jacMode != JAC_NONE) {
         for (int k = tid; k < n; k += NT) { const T g = c->packed[np + k]; c->Jy[k] = g; sq[k] = g; }
         __syncthreads();
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
         // symv(Lower, 1, JJ, deltaX, 2, Jy) with the undamped JJ, then pred = -Jy . deltaX          LS:1141-1142
         for (int i = tid; i < n; i += NT) {
             T acc = (T)0;
-            for (int j = 0; j < n; ++j) acc += c->packed[trisym(i, j)] * sdx[j];
+            for (int j = 0; j < n; ++j) acc += c->JJ[trisym(i, j)] * sdx[j];
             const T v = acc + (T)2 * c->Jy[i];
             c->Jy[i] = v; sjy[i] = v;
         }

@@ -56,9 +56,11 @@ class Engine(ReferenceAPI):
     # -- batched LM, host buffers -------------------------------------------------------
     def optimize_batched(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
                          t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
-                         fd_jacobian: bool = False, want_stats: bool = False, device: int = -1, tail_shortcut: bool = True):
+                         fd_jacobian: bool = False, want_stats: bool = False, device: int = -1, tail_shortcut: bool = True,
+                         results: np.ndarray | None = None):
         """Solve ``batch`` independent problems; x (batch, n) is updated in place.
-        l/u: shape (n,) shared, or (batch, n).  Returns (results structured array, stats dict | None)."""
+        l/u: shape (n,) shared, or (batch, n).  Returns (results structured array, stats dict | None).
+        results: optional preallocated structured array (e.g. a view of pinned memory) to receive the Result PODs."""
         sfx, real, S, R, *_ = _types(x.dtype)
         assert isinstance(settings, S)
         assert x.ndim == 2 and x.flags.c_contiguous
@@ -75,7 +77,9 @@ class Engine(ReferenceAPI):
                 flags |= MODEL_GRID_PER_PROBLEM
         assert m is not None, "m is required for data-free models"
         desc = ModelDesc(int(model), flags, _vp(t), _vp(y))
-        results = np.empty(batch, dtype=RESULT_DTYPES[x.dtype])
+        if results is None:
+            results = np.empty(batch, dtype=RESULT_DTYPES[x.dtype])
+        assert results.dtype == RESULT_DTYPES[x.dtype] and results.shape == (batch,) and results.flags.c_contiguous
         stats = BatchStats() if want_stats else None
         fn = getattr(self.lib, f"mir_optimize_least_squares_batched_{sfx}")
         rc = fn(C.byref(settings), C.byref(desc), batch, m, n, _vp(x), _vp(l), _vp(u), bound_stride,
