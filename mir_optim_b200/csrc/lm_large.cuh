@@ -287,9 +287,15 @@ __global__ void __launch_bounds__(256) large_jac_kernel(const JacArgs<T> a)
             for (int r = 0; r < LARGE_TILE; ++r) acc += tile[r * tp + tid] * sy_[r];
             myJy = acc;
         }
-        for (int e = tid; e < LARGE_TILE * ldj; e += NT) {
-            const int r = e / ldj, k = e - r * ldj;
-            if (row0 + r < a.rows) a.J[(size_t)(row0 + r) * ldj + k] = tile[r * tp + k];
+        {   // write-out: the tile is one contiguous block of J; (r, k) advance incrementally instead of a division per element
+            int r = tid / ldj, k = tid - r * ldj;
+            const int dr = NT / ldj, dk = NT - dr * ldj;
+            T* const Jt = a.J + (size_t)row0 * ldj;
+            for (int e = tid; e < LARGE_TILE * ldj; e += NT) {
+                if (row0 + r < a.rows) Jt[e] = tile[r * tp + k];
+                r += dr; k += dk;
+                if (k >= ldj) { k -= ldj; ++r; }
+            }
         }
         __syncthreads();
     }
