@@ -1,5 +1,6 @@
 // lm_batched.cu -- C ABI of the batched LM entry points (header part 2): argument checks,
 // staging of host buffers, stream-ordered scratch, launch of the warp-per-problem kernel.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -58,6 +59,8 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     // enqueued BEFORE its inputs: the per-problem inputs follow on a copy stream in chunks of 65536 problems, each
     // followed by a 4-byte watermark copy; a thread that pulls problem i from the queue waits until the watermark has
     // passed i (wait_staged).  The copy engine runs ~3x ahead of the solve, so only the first chunk's transfer is exposed.
+    // MIRB200_NO_STAGING=1: plain copy -> kernel -> copy on one stream (for tools that serialise kernels against copies)
+    static const bool noStaging = [] { const char* e = std::getenv("MIRB200_NO_STAGING"); return e && *e == '1'; }();
     const size_t chunk = 65536;
     const size_t nchunks = (batch + chunk - 1) / chunk;
     cudaStream_t cs = nullptr, ps = nullptr;
@@ -103,12 +106,13 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     CK(cudaEventRecord(ev, cs), "cudaEventRecord");
     CK(cudaStreamWaitEvent(ps, ev, 0), "cudaStreamWaitEvent");
     bool launched = false;
-    if (rc == MIR_B200_OK) {
+    auto launch = [&](const unsigned int* ready) {
         mir_model_desc dm = *model;
         dm.t = tBytes ? dt : nullptr; dm.y = yBytes ? dy : nullptr;
-        rc = batched_dev<T>(settings, &dm, batch, m, n, dx, dl, du, bound_stride, dr, stats ? ds : nullptr, cs, d_ready);
+        rc = batched_dev<T>(settings, &dm, batch, m, n, dx, dl, du, bound_stride, dr, stats ? ds : nullptr, cs, ready);
         launched = rc == MIR_B200_OK;
-    }
+    };
+    if (rc == MIR_B200_OK && !noStaging) launch(d_ready);
     // the per-problem inputs, chunk by chunk, behind the running kernel
     size_t c = 0;
     for (size_t lo = 0; lo < batch && rc == MIR_B200_OK; lo += chunk, ++c) {
@@ -123,7 +127,12 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
         h_wm[c] = (unsigned int)(lo + nb);
         CK(cudaMemcpyAsync(d_ready, &h_wm[c], sizeof(unsigned int), cudaMemcpyHostToDevice, ps), "H2D watermark");
     }
-    if (launched && rc != MIR_B200_OK) {             // a copy failed behind a running kernel: release the waiters
+    if (noStaging && rc == MIR_B200_OK) {
+        CK(cudaEventRecord(ev, ps), "cudaEventRecord");
+        CK(cudaStreamWaitEvent(cs, ev, 0), "cudaStreamWaitEvent");
+        if (rc == MIR_B200_OK) launch(nullptr);
+    }
+    if (launched && !noStaging && rc != MIR_B200_OK) {             // a copy failed behind a running kernel: release the waiters
         h_wm[nchunks] = 0xffffffffu;
         cudaMemcpyAsync(d_ready, &h_wm[nchunks], sizeof(unsigned int), cudaMemcpyHostToDevice, ps);
     }

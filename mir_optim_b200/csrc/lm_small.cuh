@@ -45,15 +45,18 @@ struct SmallBatchArgs {
 // Blocks until problem `idx` has been staged (see SmallBatchArgs::ready).  The watermark is written by the copy engine
 // (stream-ordered after the chunk's data), read here with acquire semantics at gpu scope.  Chunks are multiples of
 // 65536 problems, so no cache line of any input array straddles staged and unstaged data.  The spin is bounded
-// (~20 s) so that a failed host-side copy cannot hang the GPU.
-__device__ __forceinline__ void wait_staged(const unsigned int* ready, unsigned int idx)
+// (~20 s) so that a failed host-side copy cannot hang the GPU: on time-out the function returns false and the caller
+// reports numericError for that problem instead of solving unstaged data.  (Tools that serialise kernels against copies,
+// e.g. ncu kernel replay, starve the copy stream: run them with MIRB200_NO_STAGING=1.)
+__device__ __forceinline__ bool wait_staged(const unsigned int* ready, unsigned int idx)
 {
-    if (!ready) return;
+    if (!ready) return true;
     unsigned spins = 0;
     for (;;) {
         unsigned int v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
-        if (v > idx || ++spins > 20000000u) break;
+        if (v > idx) return true;
+        if (++spins > 20000000u) return false;
         __nanosleep(1000);
     }
 }
@@ -114,14 +117,24 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
 
     for (;;) {
         unsigned int prob32 = 0;
+        unsigned int staged = 1;
         if (glane == 0) {
             prob32 = atomicAdd(args.counter, 1u);
-            if (prob32 < args.batch) wait_staged(args.ready, prob32);
+            if (prob32 < args.batch) staged = wait_staged(args.ready, prob32) ? 1u : 0u;
         }
         prob32 = __shfl_sync(gmask, prob32, 0, LANES);
+        staged = __shfl_sync(gmask, staged, 0, LANES);
         if (prob32 >= args.batch) break;
         const unsigned long long prob = prob32;
         ++sProblems;
+        if (!staged) {                                  // inputs never arrived (host-side copy failed): fail loudly, do not touch x
+            if (glane == 0) {
+                Result bad;
+                bad.status = mir_ls_numericError; bad.iterations = 0; bad.fCalls = 0; bad.gCalls = 0; bad.residual = Num<T>::inf(); bad.lambda = (T)0;
+                static_cast<Result*>(args.results)[prob] = bad;
+            }
+            continue;
+        }
 
         // ---- load the problem ----
         T x[N], lo[N], up[N];

@@ -135,8 +135,13 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
         if (!active && !retired) {
             const unsigned int idx = atomicAdd(args.counter, 1u);
             if (idx >= args.batch) retired = true;
-            else {
-                wait_staged(args.ready, idx);
+            else if (!wait_staged(args.ready, idx)) {
+                // inputs never arrived (host-side copy failed): fail loudly, do not touch x
+                Result ret;
+                ret.status = mir_ls_numericError; ret.iterations = 0; ret.fCalls = 0; ret.gCalls = 0; ret.residual = Num<T>::inf(); ret.lambda = (T)0;
+                static_cast<Result*>(args.results)[idx] = ret;
+                ++sProblems;
+            } else {
                 prob = idx; ++sProblems;
                 const T* xp = static_cast<const T*>(args.x) + prob * N;
                 lp = static_cast<const T*>(args.l) + prob * args.bound_stride;
