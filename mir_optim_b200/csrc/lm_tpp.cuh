@@ -43,7 +43,10 @@
 
 namespace mirb200 {
 
-constexpr int TPP_THREADS = 128;
+#ifndef MIRB200_TPP_THREADS
+#define MIRB200_TPP_THREADS 128
+#endif
+constexpr int TPP_THREADS = MIRB200_TPP_THREADS;
 enum { JAC_NONE_ = 0, JAC_BROYDEN_ = 1, JAC_FRESH_ = 2 };
 enum { ROW_NONE_ = 0, ROW_EVAL_ = 1, ROW_INSTALL_ = 2 };
 
