@@ -99,3 +99,38 @@ def test_staged_chunks_per_problem_bounds_and_grids(eng, oracle_lib):
     assert np.all(rh["status"][idx] >= 0)
     er = rel_err(rh["residual"][idx], ro["residual"])
     assert np.quantile(er, 0.99) < 1e-10 and er.max() < 1e-8
+
+
+@pytest.mark.parametrize("model,n,fd", [("EXPDECAY3", 3, False), ("EXPDECAY3", 3, True), ("SUMEXP", 4, False), ("EXPTAU3", 3, False)])
+def test_other_models_and_odd_m(eng, oracle_lib, model, n, fd):
+    """n = 3 / 4 exponential models through the thread-per-problem kernel with an ODD number of samples (the row loop
+    works on pairs of rows: the last row takes the single-row tail) against the oracle, k-step trajectories."""
+    from mir_optim_b200._abi import ModelId
+    rng = np.random.default_rng(11)
+    m = 63
+    t = np.linspace(0.05, 4.0, m)
+    if model == "SUMEXP":
+        truth = np.stack([rng.uniform(1, 3, B), rng.uniform(0.3, 0.6, B), rng.uniform(1, 3, B), rng.uniform(1.5, 2.5, B)], axis=1)
+        clean = truth[:, 0:1] * np.exp(-truth[:, 1:2] * t) + truth[:, 2:3] * np.exp(-truth[:, 3:4] * t)
+    elif model == "EXPTAU3":
+        truth = np.stack([rng.uniform(1, 3, B), rng.uniform(0.5, 2.0, B), rng.uniform(0, 1, B)], axis=1)
+        clean = truth[:, 0:1] * np.exp(-t / truth[:, 1:2]) + truth[:, 2:3]
+    else:
+        truth = np.stack([rng.uniform(1, 3, B), rng.uniform(0.3, 1.5, B), rng.uniform(0, 1, B)], axis=1)
+        clean = truth[:, 0:1] * np.exp(-truth[:, 1:2] * t) + truth[:, 2:3]
+    y = clean + 0.01 * rng.standard_normal((B, m))
+    x0 = truth * rng.uniform(0.85, 1.15, truth.shape)
+    l = np.full(n, -np.inf); u = np.full(n, np.inf)
+    mid = getattr(ModelId, model)
+    for k in (1, 3):
+        sg = eng.settings(); so = eng.settings()
+        sg.maxIterations = k; so.maxIterations = k
+        xg = x0.copy()
+        rg, _ = eng.optimize_batched(sg, mid, xg, l, u, t=t, y=y, fd_jacobian=fd)
+        xo, ro, _ = oracle_batched_mp(oracle_lib, so, mid, x0, l, u, t=t, y=y, fd_jacobian=fd)
+        same = ((rg["status"] == ro["status"]) & (rg["iterations"] == ro["iterations"]) & (rg["fCalls"] == ro["fCalls"])
+                & (rg["gCalls"] == ro["gCalls"]))
+        assert same.mean() >= 0.999, (model, fd, k, float(same.mean()))
+        tol = 1e-8 if fd else 1e-11
+        assert np.max(rel_err(xg[same], xo[same])) < tol, (model, fd, k)
+        assert np.max(rel_err(rg["residual"][same], ro["residual"][same])) < tol * 20, (model, fd, k)
