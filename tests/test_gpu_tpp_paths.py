@@ -134,3 +134,24 @@ def test_other_models_and_odd_m(eng, oracle_lib, model, n, fd):
         tol = 1e-8 if fd else 1e-11
         assert np.max(rel_err(xg[same], xo[same])) < tol, (model, fd, k)
         assert np.max(rel_err(rg["residual"][same], ro["residual"][same])) < tol * 20, (model, fd, k)
+
+
+def test_cuda_path_matches_golden_fixture(eng):
+    """tests/golden/oracle_c2_k3.json (scripts/make_golden.py): the committed oracle outputs, checked here without the oracle."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_c2_k3.json")))
+    k3 = g["k3"]
+    wl = workloads.c2_gauss4(24, noise=k3["noise"], seed=k3["seed"])
+    s = eng.settings(); s.maxIterations = k3["maxIterations"]
+    x = wl.x0.copy()
+    r, _ = eng.optimize_batched(s, wl.model, x, wl.l, wl.u, t=wl.t, y=wl.y)
+    for f in ("status", "iterations", "fCalls", "gCalls"):
+        assert r[f].tolist() == k3[f], f
+    assert np.max(rel_err(x, np.array(k3["x"]))) < 1e-12 and np.max(rel_err(r["residual"], np.array(k3["residual"]))) < 1e-11
+    rb = g["robust"]
+    wl = workloads.c2_gauss4(24, noise=rb["noise"], seed=rb["seed"])
+    s = eng.settings(); s.maxGoodResidual = rb["maxGoodResidual"]
+    x = wl.x0.copy()
+    r, _ = eng.optimize_batched(s, wl.model, x, np.array(rb["l"]), np.array(rb["u"]), t=wl.t, y=wl.y)
+    assert r["status"].tolist() == rb["status"] and r["iterations"].tolist() == rb["iterations"] and r["gCalls"].tolist() == rb["gCalls"]
+    assert np.max(rel_err(x, np.array(rb["x"]))) < 1e-10
