@@ -42,13 +42,13 @@ static __constant__ float kExpS[11] = {
 template <int K>
 static __device__ __forceinline__ void exp_repro_many(const double* __restrict__ x, double* __restrict__ e)
 {
-    double xc[K], k[K], r[K], p[K];
+    // No clamping of the argument: for x outside [-745.2, 709.78] (or NaN) the polynomial path produces garbage
+    // (the float -> int conversion saturates, nothing traps) that the final selects replace.
+    double k[K], r[K], p[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) xc[j] = fmin(fmax(x[j], -746.0), 710.0);
+    for (int j = 0; j < K; ++j) k[j] = rint(__dmul_rn(x[j], kExpD[0]));
 #pragma unroll
-    for (int j = 0; j < K; ++j) k[j] = rint(__dmul_rn(xc[j], kExpD[0]));
-#pragma unroll
-    for (int j = 0; j < K; ++j) r[j] = fma(-k[j], kExpD[1], xc[j]);
+    for (int j = 0; j < K; ++j) r[j] = fma(-k[j], kExpD[1], x[j]);
 #pragma unroll
     for (int j = 0; j < K; ++j) r[j] = fma(-k[j], kExpD[2], r[j]);
 #pragma unroll
@@ -61,9 +61,9 @@ static __device__ __forceinline__ void exp_repro_many(const double* __restrict__
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        const int ki = (int)k[j], h = ki >> 1;
-        const double s1 = __hiloint2double((h + 1023) << 20, 0);
-        const double s2 = __hiloint2double((ki - h + 1023) << 20, 0);
+        const int ki = __double2int_rn(k[j]), h = ki >> 1;                  // saturating conversion: defined for any k
+        const double s1 = __hiloint2double((int)((unsigned)(h + 1023) << 20), 0);
+        const double s2 = __hiloint2double((int)((unsigned)(ki - h + 1023) << 20), 0);
         double v = __dmul_rn(__dmul_rn(p[j], s1), s2);
         v = (x[j] > 709.782712893384) ? Num<double>::inf() : v;
         e[j] = (x[j] > -745.2) ? v : ((x[j] == x[j]) ? 0.0 : x[j]);
@@ -73,13 +73,11 @@ static __device__ __forceinline__ void exp_repro_many(const double* __restrict__
 template <int K>
 static __device__ __forceinline__ void exp_repro_many(const float* __restrict__ x, float* __restrict__ e)
 {
-    float xc[K], k[K], r[K], p[K];
+    float k[K], r[K], p[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) xc[j] = fminf(fmaxf(x[j], -105.0f), 89.0f);
+    for (int j = 0; j < K; ++j) k[j] = rintf(__fmul_rn(x[j], kExpS[0]));
 #pragma unroll
-    for (int j = 0; j < K; ++j) k[j] = rintf(__fmul_rn(xc[j], kExpS[0]));
-#pragma unroll
-    for (int j = 0; j < K; ++j) r[j] = fmaf(-k[j], kExpS[1], xc[j]);
+    for (int j = 0; j < K; ++j) r[j] = fmaf(-k[j], kExpS[1], x[j]);
 #pragma unroll
     for (int j = 0; j < K; ++j) r[j] = fmaf(-k[j], kExpS[2], r[j]);
 #pragma unroll
@@ -92,9 +90,9 @@ static __device__ __forceinline__ void exp_repro_many(const float* __restrict__ 
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        const int ki = (int)k[j], h = ki >> 1;
-        const float s1 = __int_as_float((h + 127) << 23);
-        const float s2 = __int_as_float((ki - h + 127) << 23);
+        const int ki = __float2int_rn(k[j]), h = ki >> 1;
+        const float s1 = __int_as_float((int)((unsigned)(h + 127) << 23));
+        const float s2 = __int_as_float((int)((unsigned)(ki - h + 127) << 23));
         float v = __fmul_rn(__fmul_rn(p[j], s1), s2);
         v = (x[j] > 88.72284f) ? Num<float>::inf() : v;
         e[j] = (x[j] > -104.0f) ? v : ((x[j] == x[j]) ? 0.0f : x[j]);
