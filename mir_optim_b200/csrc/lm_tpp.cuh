@@ -387,20 +387,20 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                     d1[i] = (kB && k > 1) ? DL(1, i) : (T)0;
                 }
                 const typename Model::Pre preA = Model::prepare(anchor);
-                struct RowIn { T tt, yo, fo, v0, v1; };
+                // slab values are loaded a pair of rows ahead (global-memory latency); abscissa and observation come from
+                // shared memory at compute time
+                struct RowIn { T fo, v0, v1; };
                 auto rowLoad = [&](int row, RowIn& in, bool on) {
-                    in.tt = (Model::kHasData && on) ? tp[row] : (T)0;
-                    in.yo = (Model::kHasData && on) ? YO(row) : (T)0;
                     in.fo = (kB && on) ? fold[row * NT] : (T)0;
                     in.v0 = (kB && k > 0 && on) ? pV[row * NT] : (T)0;
                     in.v1 = (kB && k > 1 && on) ? pV[(size_t)m * NT + row * NT] : (T)0;
                 };
                 // Branch-free: every lane runs the Broyden arithmetic (selects pick the result, loads and stores are
                 // predicated).  eT / eA: the exps of this row at the trial point and at the anchor.
-                auto rowFinish = [&](int row, const RowIn& in, const T* eT, const T* eA, bool on) {
+                auto rowFinish = [&](int row, const RowIn& in, T tt, T yo, const T* eT, const T* eA, bool on) {
                     T r, Jf[N], Jr[N], Jn[N];
-                    Model::finish_rj(pre, xt, in.tt, in.yo, eT, r, Jf);               // f and the fresh-Jacobian candidate
-                    Model::finish_j(preA, anchor, in.tt, eA, Jr);                     // g_row(x_anchor), then the accepted terms
+                    Model::finish_rj(pre, xt, tt, yo, eT, r, Jf);                     // f and the fresh-Jacobian candidate
+                    Model::finish_j(preA, anchor, tt, eA, Jr);                        // g_row(x_anchor), then the accepted terms
                     // Terms beyond the list length have v = 0 and d = 0 (rowLoad / d0, d1 above), so applying both terms
                     // unconditionally changes nothing but the sign of an exact zero entry (-0 + (+0) = +0).  A zero of J only
                     // ever meets the accumulators below through products that are themselves zeros, and an accumulator that
@@ -431,12 +431,15 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                 };
                 // A pair of rows: four independent exp batches (2 rows x {trial point, anchor}) in one interleaved call.
                 auto pairCompute = [&](int row, const RowIn& A, const RowIn& B, bool two) {
+                    const int rowB = two ? row + 1 : row;
+                    const T ta = Model::kHasData ? tp[row] : (T)0, ya = Model::kHasData ? YO(row) : (T)0;
+                    const T tb = Model::kHasData ? tp[rowB] : (T)0, yb = Model::kHasData ? YO(rowB) : (T)0;
                     T ea[4 * NE], ee[4 * NE];
-                    Model::exp_args(pre, xt, A.tt, ea); Model::exp_args(pre, xt, B.tt, ea + NE);
-                    Model::exp_args(preA, anchor, A.tt, ea + 2 * NE); Model::exp_args(preA, anchor, B.tt, ea + 3 * NE);
+                    Model::exp_args(pre, xt, ta, ea); Model::exp_args(pre, xt, tb, ea + NE);
+                    Model::exp_args(preA, anchor, ta, ea + 2 * NE); Model::exp_args(preA, anchor, tb, ea + 3 * NE);
                     exp_repro_many<4 * NE>(ea, ee);
-                    rowFinish(row, A, ee, ee + 2 * NE, true);
-                    rowFinish(row + 1, B, ee + NE, ee + 3 * NE, two);
+                    rowFinish(row, A, ta, ya, ee, ee + 2 * NE, true);
+                    rowFinish(row + 1, B, tb, yb, ee + NE, ee + 3 * NE, two);
                 };
                 int row = 0;
                 RowIn ra, rb;
