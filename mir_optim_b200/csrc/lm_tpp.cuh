@@ -456,20 +456,18 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
             } else {
                 // Stored-J scheme.  One row = slab/shared loads (issued a pair of rows ahead: their latency hides behind
                 // the previous pair's exp chains) + compute.
-                struct RowIn { T tt, yo, fo, vp; T Jr[N]; };
+                struct RowIn { T fo, vp; T Jr[N]; };
                 auto rowLoad = [&](int row, RowIn& in, bool on) {
-                    in.tt = (Model::kHasData && on) ? tp[row] : (T)0;
-                    in.yo = (Model::kHasData && on) ? YO(row) : (T)0;
 #pragma unroll
                     for (int i = 0; i < N; ++i) in.Jr[i] = (kB && on) ? JE(row, i) : (T)0;
                     in.fo = (kB && on) ? fold[row * NT] : (T)0;
                     in.vp = (pnd && on) ? pV[row * NT] : (T)0;
                 };
-                auto rowFinish = [&](int row, RowIn& in, const T* eT, bool on) {
+                auto rowFinish = [&](int row, RowIn& in, T tt, T yo, const T* eT, bool on) {
                     T r, Jn[N];
-                    if constexpr (!FD) Model::finish_rj(pre, xt, in.tt, in.yo, eT, r, Jn);   // f and the fresh-Jacobian candidate
+                    if constexpr (!FD) Model::finish_rj(pre, xt, tt, yo, eT, r, Jn);         // f and the fresh-Jacobian candidate
                     else {
-                        Model::finish_r(pre, xt, in.tt, in.yo, eT, r);
+                        Model::finish_r(pre, xt, tt, yo, eT, r);
 #pragma unroll
                         for (int i = 0; i < N; ++i) Jn[i] = (T)0;
                     }
@@ -506,11 +504,14 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                     }
                 };
                 auto pairCompute = [&](int row, RowIn& A, RowIn& B, bool two) {
+                    const int rowB = two ? row + 1 : row;
+                    const T ta = Model::kHasData ? tp[row] : (T)0, ya = Model::kHasData ? YO(row) : (T)0;
+                    const T tb = Model::kHasData ? tp[rowB] : (T)0, yb = Model::kHasData ? YO(rowB) : (T)0;
                     T ea[2 * NE], ee[2 * NE];
-                    Model::exp_args(pre, xt, A.tt, ea); Model::exp_args(pre, xt, B.tt, ea + NE);
+                    Model::exp_args(pre, xt, ta, ea); Model::exp_args(pre, xt, tb, ea + NE);
                     exp_repro_many<2 * NE>(ea, ee);
-                    rowFinish(row, A, ee, true);
-                    rowFinish(row + 1, B, ee + NE, two);
+                    rowFinish(row, A, ta, ya, ee, true);
+                    rowFinish(row + 1, B, tb, yb, ee + NE, two);
                 };
                 int row = 0;
                 RowIn ra, rb;
