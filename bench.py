@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20, help="fits per GPU per step (weak scaling)")
     ap.add_argument("--noise", type=float, default=0.05)
-    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--cpu-sample", type=int, default=32768)
     ap.add_argument("--ref-sample", type=int, default=65536)
     ap.add_argument("--ref-step-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
