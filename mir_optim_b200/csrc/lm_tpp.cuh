@@ -50,6 +50,11 @@ constexpr int TPP_THREADS = MIRB200_TPP_THREADS;
 enum { JAC_NONE_ = 0, JAC_BROYDEN_ = 1, JAC_FRESH_ = 2 };
 enum { ROW_NONE_ = 0, ROW_EVAL_ = 1, ROW_INSTALL_ = 2 };
 
+// Experimental (off): warp-cooperative, coalesced refill of the observations through an out-of-line helper.  The inline
+// form was parity-green on B200 but 20 % slower (it disturbed the register allocation of the row loop); see DESIGN 7.
+#ifndef MIRB200_TPP_COOP_REFILL
+#define MIRB200_TPP_COOP_REFILL 0
+#endif
 #ifndef MIRB200_TPP_MINBLOCKS
 #define MIRB200_TPP_MINBLOCKS 1
 #endif
@@ -59,6 +64,24 @@ enum { ROW_NONE_ = 0, ROW_EVAL_ = 1, ROW_INSTALL_ = 2 };
 // (stored-J scheme: [yobs] buf0 buf1 v + m x N Jacobian;  v-list scheme: [yobs] buf0 buf1 v0 v1 v2, no Jacobian)
 constexpr int TPP_VLN = 3;          // Broyden terms the v-list scheme can hold = largest maxAge it serves
 template <int N, bool YOS, bool VL> struct TppSlab { static constexpr int ELEMS = (YOS ? 2 : 3) + (VL ? TPP_VLN : 1 + N); };
+
+#if MIRB200_TPP_COOP_REFILL
+// Every lane whose bit is set in `need` started problem `prob` (its own value) in this pass: the whole warp copies that
+// problem's m samples (coalesced reads) into the lane's column `col0 + lane'` ([row][thread] layout, pitch NT).
+template <class T>
+__device__ __noinline__ void tpp_refill_observations(unsigned need, unsigned long long prob, const T* yptr, int m, T* col0, int lane)
+{
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const unsigned long long p = __shfl_sync(0xffffffffu, prob, src);
+        const T* yp = yptr + p * (unsigned long long)m;
+        T* const col = col0 + src;
+        for (int row = lane; row < m; row += 32) col[row * TPP_THREADS] = yp[row];
+    }
+    __syncwarp();
+}
+#endif
 
 // YOS: the observations of the thread's current problem live in shared memory ([row][thread], conflict-free)
 // instead of the slab -- they are read by every model evaluation, the most frequent phase.
@@ -135,6 +158,9 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
 
     for (;;) {
         // ------------------------------------------------------------------ fetch
+#if MIRB200_TPP_COOP_REFILL
+        bool started = false;
+#endif
         if (!active && !retired) {
             const unsigned int idx = atomicAdd(args.counter, 1u);
             if (idx >= args.batch) retired = true;
@@ -173,11 +199,15 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                 } else {
                     active = true; init = true; resume = false; specOK = false; pend = false; nterm = 0; specKind = JAC_NONE_;
                     tp = gridPerProblem ? tptr + prob * (unsigned long long)m : st_;
+#if MIRB200_TPP_COOP_REFILL
+                    started = true;
+#else
                     if (Model::kHasData) {
                         const T* yp = yptr + prob * (unsigned long long)m;
 #pragma unroll 8
                         for (int row = 0; row < m; ++row) YO(row) = yp[row];
                     }
+#endif
 #pragma unroll
                     for (int i = 0; i < N; ++i) { xt[i] = x[i]; Jy[i] = (T)0; dX[i] = (T)0; }
                     maxAge = st.maxAge ? st.maxAge : (FD ? 2u * N : 3u);                             // LS:945
@@ -187,6 +217,12 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                 }
             }
         }
+#if MIRB200_TPP_COOP_REFILL
+        if (Model::kHasData) {
+            const unsigned need = __ballot_sync(0xffffffffu, started);
+            if (need) tpp_refill_observations<T>(need, prob, yptr, m, pYO - (tid & 31), tid & 31);
+        }
+#endif
         if (__all_sync(0xffffffffu, retired)) break;
 
         // ------------------------------------------------------------------ guards of this pass, LS:974-995, and the Jacobian decision, LS:996-1015
