@@ -236,6 +236,54 @@ def secondary_c4(torch, dist, eng, dev, workloads, sharding, rank, world, m=4_00
     return out
 
 
+def secondary_cpu_baselines(workloads, c4_m=4_000_000):
+    """The CPU oracle (restated reference + real LAPACK/CBLAS from OpenBLAS) on bounded samples of the secondary configs,
+    all host cores, timed on this box in the same run (rank 0, N = 1 only).  Reported baselines, not targets."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_oracle
+    from oracle_util import oracle_batched, oracle_batched_mp, oracle_box_qp_batched_mp
+    from mir_optim_b200.api import ReferenceAPI
+    lib = load_oracle(); api = ReferenceAPI(lib)
+    cores = os.cpu_count() or 1
+    out = {}
+    for name, dt in (("c3_sumexp8_f64", np.float64), ("c3_sumexp8_f32", np.float32)):
+        n_s = 2048
+        wl = workloads.c3_sumexp8(n_s, dtype=dt, seed=3)
+        t0 = time.perf_counter()
+        _, res, procs = oracle_batched_mp(lib, api.settings(dt), wl.model, wl.x0, wl.l, wl.u, t=wl.t, y=wl.y, fd_jacobian=True)
+        secs = time.perf_counter() - t0
+        out[name] = {"value": n_s / secs, "unit": "fits/s", "cores": procs, "kind": "port",
+                     "sample": f"{n_s} fits of the same generator ({secs:.1f} s), one forked single-threaded-OpenBLAS worker per core",
+                     "frac_status_ok": float(np.mean(res["status"] >= 0))}
+    n_q = 8192
+    wl = workloads.c5_boxqp(n_q, bound_scale=2.0)
+    t0 = time.perf_counter()
+    _, st, it, procs = oracle_box_qp_batched_mp(lib, wl.P, wl.q, wl.l, wl.u)
+    secs = time.perf_counter() - t0
+    out["c5a_boxqp_n64_f64"] = {"value": n_q / secs, "unit": "QP/s", "cores": procs, "kind": "port",
+                                "sample": f"{n_q} QPs (n = 64, P = A'A/256 + 0.1 I, bounds +-U(0,2)) ({secs:.1f} s), one forked worker per core",
+                                "mean_boxcqp_iterations": float(it.mean()), "frac_solved": float(np.mean(st == 0))}
+    # configs[3]: ONE problem at the full size; OpenBLAS and the model callbacks use all cores.  Bounded by
+    # maxIterations = 2 (the per-pass cost does not depend on the pass index: same J^T J, same rank-1 update, same evaluation)
+    wl = workloads.c4_gaussmix(m=c4_m)
+    s = api.settings(np.float64); s.maxIterations = 2
+    lib.oracle_set_blas_threads(cores)
+    lib.oracle_counters_reset()
+    t0 = time.perf_counter()
+    _, res, _ = oracle_batched(lib, s, wl.model, wl.x0, wl.l, wl.u, t=wl.t, y=wl.y.reshape(1, -1))
+    secs = time.perf_counter() - t0
+    lib.oracle_set_blas_threads(1)
+    import ctypes as C
+    p_ = C.c_ulonglong(); q_ = C.c_ulonglong()
+    lib.oracle_counters(C.byref(p_), C.byref(q_))
+    passes = max(int(p_.value), 1)
+    out["c4_gaussmix_4Mx128_f64"] = {"value": int(res["iterations"][0]) / secs, "unit": "LM iterations/s", "cores": cores, "kind": "port",
+                                     "passes_per_s": passes / secs, "passes": passes, "iterations": int(res["iterations"][0]),
+                                     "sample": f"the same {c4_m} x 128 problem, first 2 accepted steps ({passes} passes, {secs:.1f} s): "
+                                               f"OpenBLAS dsyrk/dgemv/dger with {cores} threads, model callbacks OpenMP over rows"}
+    return out
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference algorithm (CPU oracle: restated LM/BOXCQP + real LAPACK ?posvx from
     OpenBLAS; the D reference itself cannot be built here -- no D compiler) on all host cores."""
@@ -459,6 +507,14 @@ def main():
         cpu = {"value": rate, "unit": "fits/s", "cores": threads, "kind": "port",
                "sample": f"first {sample} of the {B} fits of one step ({secs:.1f} s), one forked worker process per core over problems, OpenBLAS 1 thread/worker, "
                          f"host has {os.cpu_count()} logical cores; oracle = restated least_squares.d:877-1176 + real LAPACK dposvx"}
+
+    if secondary is not None and world == 1 and not args.no_cpu_baseline:
+        try:
+            for k, v in secondary_cpu_baselines(workloads).items():
+                if k in secondary:
+                    secondary[k]["cpu_baseline"] = v
+        except Exception as e:                       # noqa: BLE001
+            secondary["cpu_baseline_error"] = repr(e)
 
     line = {"metric": "LM problems solved/sec (batched)", "value": value, "unit": "fits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,

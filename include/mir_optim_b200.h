@@ -354,6 +354,18 @@ int mir_optimize_least_squares_sharded_d(
  * by rows, n(n+1)/2 doubles (device).  Asynchronous on cuda_stream.  For roofline measurements and tests. */
 int mir_b200_syrk_lower_dev_d(const double* J, size_t rows, size_t n, size_t ldj, double* packed, void* cuda_stream);
 
+/* Diagnostics: the device restatements of LAPACK ?posvx(FACT='E', UPLO='L') -- what solveBoxQP calls at BQ:194-205
+ * and BQ:310-321 -- on their own, for unit tests against the real LAPACK routine.  A T[batch*n*n] row-major (lower
+ * triangle read), b / x T[batch*n], info int32[batch] (0, or k > 0: factorisation broke down at pivot k; LAPACK's
+ * info = n+1 "singular to working precision", which BQ:212/323 accepts, is reported as 0), equed int32[batch]
+ * (1 = the ?laqsy equilibration was applied).  variant 0: register-resident solver of the batched LM kernels
+ * (n <= 8); 1: shared-memory column loop of the batched BoxQP kernel; 2: blocked solver of the large-problem
+ * control kernel (both n <= 128).  Host pointers, synchronous. */
+int mir_b200_posvx_batched_d(int variant, size_t batch, size_t n, const double* A, const double* b, double* x,
+                             int32_t* info, int32_t* equed, int device);
+int mir_b200_posvx_batched_s(int variant, size_t batch, size_t n, const float* A, const float* b, float* x,
+                             int32_t* info, int32_t* equed, int device);
+
 /* NCCL bootstrap helpers so that a host runtime without NCCL bindings (ctypes, D) can build the
  * communicator: rank 0 calls get_unique_id (128 bytes), shares it by any means, all call init. */
 int  mir_b200_nccl_unique_id(void* id128);

@@ -136,6 +136,7 @@ B200_SYMBOLS = [
     "mir_solve_box_qp_batched_d", "mir_solve_box_qp_batched_s",
     "mir_solve_box_qp_batched_dev_d", "mir_solve_box_qp_batched_dev_s",
     "mir_optimize_least_squares_sharded_d", "mir_b200_syrk_lower_dev_d",
+    "mir_b200_posvx_batched_d", "mir_b200_posvx_batched_s",
     "mir_b200_nccl_unique_id", "mir_b200_nccl_comm_init", "mir_b200_nccl_comm_destroy",
 ]
 
@@ -187,6 +188,9 @@ def bind_b200_abi(lib):
     fn.restype = C.c_int
     lib.mir_b200_syrk_lower_dev_d.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, vp]
     lib.mir_b200_syrk_lower_dev_d.restype = C.c_int
+    for sfx in ("d", "s"):
+        fn = getattr(lib, f"mir_b200_posvx_batched_{sfx}")
+        fn.argtypes = [C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, vp, vp, C.c_int]; fn.restype = C.c_int
     lib.mir_b200_nccl_unique_id.argtypes = [vp]; lib.mir_b200_nccl_unique_id.restype = C.c_int
     lib.mir_b200_nccl_comm_init.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int]; lib.mir_b200_nccl_comm_init.restype = C.c_int
     lib.mir_b200_nccl_comm_destroy.argtypes = [vp]; lib.mir_b200_nccl_comm_destroy.restype = C.c_int

@@ -261,7 +261,7 @@ __device__ __forceinline__ void cta_ldl_solve_blocked(int s, const T* F, int ldf
 // that matters (the LM control kernel, n = 128: 0.47 -> 0.22 ms); the batched BoxQP kernel, with two CTAs per SM
 // competing for issue slots, is faster with the all-threads column loop (measured 1.35 M vs 1.17 M QP/s at n = 64).
 template <class T, int NT, bool BLK, class AGet>
-__device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
+__device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x, int* equed_out = nullptr)
 {
     const int tid = threadIdx.x;
     T* F = w.F; const int ldf = w.ldf;
@@ -276,6 +276,7 @@ __device__ int cta_posvx(int s, AGet A, CtaQPScratch<T>& w, T* b, T* x)
         const T scond = sqrt_ni(smin) / sqrt_ni(amax);
         equil = !(scond >= (T)0.1 && amax >= Num<T>::small_() && amax <= Num<T>::large_());
     }
+    if (equed_out && tid == 0) *equed_out = equil ? 1 : 0;      // (unit tests only: the ?laqsy decision, LAPACK's EQUED)
     for (int a = tid; a < s; a += NT) {
         const T sa = equil ? (T)1 / sqrt_ni(A(a, a)) : (T)1;
         w.sc[a] = sa;

@@ -31,7 +31,7 @@ template <int N> struct FullMask { static constexpr unsigned value = (N >= 32) ?
 // unconstrained solve (free = all ones) and the active-set solves, to keep the code small.
 template <class T, int N>
 __device__ __forceinline__ int posvx_small(const T (&JJ)[N * (N + 1) / 2], T lambda, unsigned free,
-                                           const T (&b_in)[N], T (&x)[N])
+                                           const T (&b_in)[N], T (&x)[N], bool* equed_out = nullptr)
 {
     constexpr int NP = N * (N + 1) / 2;
     T a[NP];      // (equilibrated) system matrix, packed lower
@@ -65,6 +65,7 @@ __device__ __forceinline__ int posvx_small(const T (&JJ)[N * (N + 1) / 2], T lam
         else wellScaled = div_ni(sqrt_ni(smin), sqrt_ni(amax)) >= (T)0.1;
         equil = !(wellScaled && amax >= Num<T>::small_() && amax <= Num<T>::large_());
     }
+    if (equed_out) *equed_out = equil;          // (unit tests only: the ?laqsy decision, LAPACK's EQUED)
     if (equil) {
 #pragma unroll
         for (int i = 0; i < N; ++i) s[i] = ((free >> i) & 1u) ? rcp_ni(sqrt_ni(a[tri(i, i)])) : (T)1;

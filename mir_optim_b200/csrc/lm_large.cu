@@ -258,7 +258,7 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
     h->tailShortcut = (modelFlags & MIR_MODEL_NO_TAIL_SHORTCUT) ? 0 : 1;
     h->maxAge = st.maxAge ? st.maxAge : (hasG ? 3u : 2u * (unsigned)n);                           // LS:945
     h->status = mir_ls_maxIterations; h->residual = Num<T>::inf();
-    h->initPhase = 1; h->doEval = 1; h->ysel = 0; h->mu = 1;
+    h->initPhase = 1; h->doEval = 1; h->ysel = 0; h->mu = 1; h->chunkSeq = 0; h->doneChunk = -1;
     for (int i = 0; i < n; ++i) { h->x[i] = x[i]; h->xt[i] = x[i]; h->l[i] = l[i]; h->u[i] = u[i]; }
     MIRB200_CUDA(cudaMemcpyAsync(d_ctl, h.get(), sizeof(Ctl), cudaMemcpyHostToDevice, stream));
 
@@ -353,7 +353,7 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
     // ---- passes: enqueued in chunks, `done` polled one chunk behind ----
     int* h_done = static_cast<int*>(pinned_scratch(2 * sizeof(int)));
     if (!h_done) { set_error("mir_optim_b200: cannot allocate pinned host scratch"); return MIR_B200_ECUDA; }
-    h_done[0] = h_done[1] = 0;
+    h_done[0] = h_done[1] = -1;
     cudaEvent_t ev[2];
     MIRB200_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     MIRB200_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
@@ -366,8 +366,11 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
             if (int r = step_eval()) return r;
             if (int r = step_post()) return r;
         }
-        // `done` only ever goes 0 -> 1, so one host slot serves every chunk
-        return check_cuda(cudaMemcpyAsync(&h_done[0], (char*)d_ctl + offsetof(Ctl, done), sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H done");
+        // The mailbox carries the index of the chunk in which the solve finished (-1 while it runs), see
+        // large_chunk_end_kernel: one host slot serves every chunk and the stop decision below is the same on every
+        // rank no matter how late its host reads the slot.
+        large_chunk_end_kernel<T><<<1, 1, 0, stream>>>(d_ctl); count_launch();
+        return check_cuda(cudaMemcpyAsync(&h_done[0], (char*)d_ctl + offsetof(Ctl, doneChunk), sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H done");
     };
     // Every kernel of a pass takes its arguments from the device-resident control block, so a chunk of passes is the
     // same ~40 launches (+ all-reduces) every time: captured once and replayed as a CUDA graph, the host issues one
@@ -398,8 +401,14 @@ static int large_solve(const typename Num<T>::Settings& st, unsigned model, unsi
         else if ((rc = enqueue_chunk())) return rc;
         const int slot = (int)(c & 1);
         MIRB200_CUDA(cudaEventRecord(ev[slot], stream));
-        if (cb) { MIRB200_CUDA(cudaEventSynchronize(ev[slot])); finished = h_done[0] != 0; }
-        else if (c >= 1) { MIRB200_CUDA(cudaEventSynchronize(ev[slot ^ 1])); finished = h_done[0] != 0; }
+        // decide from the state at the end of the chunk that was synchronised on, and from nothing later: every rank
+        // of a sharded run then enqueues exactly doneChunk + 2 chunks (the last one a no-op whose all-reduces still pair up)
+        if (cb) { MIRB200_CUDA(cudaEventSynchronize(ev[slot])); finished = h_done[0] >= 0; }
+        else if (c >= 1) {
+            MIRB200_CUDA(cudaEventSynchronize(ev[slot ^ 1]));
+            const int dc = *(volatile int*)&h_done[0];
+            finished = dc >= 0 && (unsigned long long)dc <= c - 1;
+        }
     }
 
     TR("passes");

@@ -49,6 +49,7 @@ template <class T> struct LargeCtl {
     // per-pass flags
     int jacMode, doEval, skipRest, done, ysel, initPhase;
     unsigned int ticket[4];      // last-block tickets of the row-parallel kernels
+    int chunkSeq, doneChunk;     // chunks of passes completed so far; index of the chunk in which `done` was raised (-1: still running)
     unsigned long long passes, accepted, fresh, broyden, evals, qpSolves, qpIters;
     T rr;                        // ||f(trial)||^2 (all-reduced in place)
     T x[LARGE_NMAX], xt[LARGE_NMAX], l[LARGE_NMAX], u[LARGE_NMAX], dX[LARGE_NMAX], Jy[LARGE_NMAX];
@@ -90,7 +91,9 @@ template <class T> __device__ void large_begin_pass(LargeCtl<T>* c)
         // inert lambda-overflow tail (proof at tail_is_inert in lm_small.cuh): replay the scalar recurrence only
         T q2 = (T)0, xmin = Num<T>::inf();
         for (int i = 0; i < c->n; ++i) { q2 += c->Jy[i] * c->Jy[i]; xmin = t_min(xmin, t_abs(c->x[i])); }
-        if (xmin > (T)0 && sqrt_ni(q2) < c->lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125))) {
+        bool inside = c->st.maxStep > (T)0;           // + no x_i on a bound, + LS:1101 cannot pre-empt the evaluation (see tail_is_inert)
+        for (int i = 0; i < c->n; ++i) inside = inside && (c->l[i] < c->x[i]) && (c->x[i] < c->u[i]);
+        if (inside && xmin > (T)0 && sqrt_ni(q2) < c->lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125))) {
             for (;;) {
                 ++c->fCalls;
                 c->lambda *= c->st.lambdaIncrease * c->mu; c->mu *= (T)2;
@@ -109,6 +112,16 @@ template <class T> __device__ void large_begin_pass(LargeCtl<T>* c)
             else c->fCalls += (unsigned)c->n;                                                      // LS:1049
         }
     }
+}
+
+// Last node of every chunk of passes.  The host enqueues chunks blindly and polls one chunk behind; what it polls is
+// doneChunk, the index of the chunk in which the solve finished, never a bare flag: a rank of a row-sharded run whose
+// host happens to read the mailbox late (after the NEXT chunk's copy landed) must still take the decision that belongs
+// to the chunk it synchronised on, or ranks would enqueue different numbers of chunks -- and of all-reduces.
+template <class T> __global__ void large_chunk_end_kernel(LargeCtl<T>* c)
+{
+    if (c->done && c->doneChunk < 0) c->doneChunk = c->chunkSeq;
+    ++c->chunkSeq;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -32,9 +32,10 @@ struct SmallBatchArgs {
     const void* u;
     void*       results;    // Result[batch]
     unsigned int* counter;         // work queue head (zeroed by the launcher); batch < 2^32 per launch
-    const unsigned int* ready;     // null, or a watermark: problems [0, *ready) have been staged into device memory.  The
-                                   // host-pointer entry launches the kernel first and copies the inputs behind it in chunks,
-                                   // bumping the watermark after each chunk, so the transfer overlaps the solve.
+    const unsigned int* ready;     // null, or {watermark, time-out flag}: problems [0, ready[0]) have been staged into device
+                                   // memory.  The host-pointer entry copies the inputs in chunks, bumping the watermark after
+                                   // each chunk, and runs the kernel beside the copies, so the transfer overlaps the solve.
+    unsigned int spin_limit;       // wait_staged gives up after this many ~1 us polls of one problem
     mir_batch_stats* stats; // may be null
     unsigned long long batch;
     unsigned m;
@@ -42,21 +43,27 @@ struct SmallBatchArgs {
     unsigned flags;         // MIR_MODEL_* flags
 };
 
-// Blocks until problem `idx` has been staged (see SmallBatchArgs::ready).  The watermark is written by the copy engine
-// (stream-ordered after the chunk's data), read here with acquire semantics at gpu scope.  Chunks are multiples of
-// 65536 problems, so no cache line of any input array straddles staged and unstaged data.  The spin is bounded
-// (~20 s) so that a failed host-side copy cannot hang the GPU: on time-out the function returns false and the caller
-// reports numericError for that problem instead of solving unstaged data.  (Tools that serialise kernels against copies,
-// e.g. ncu kernel replay, starve the copy stream: run them with MIRB200_NO_STAGING=1.)
-__device__ __forceinline__ bool wait_staged(const unsigned int* ready, unsigned int idx)
+// Blocks until problem `idx` has been staged (see SmallBatchArgs::ready).  ready[0] is the watermark, written by the
+// copy engine (stream-ordered after the chunk's data) and read here with acquire semantics at gpu scope; ready[1] is a
+// time-out flag owned by the kernel.  Chunks are multiples of 65536 problems, so no cache line of any input array
+// straddles staged and unstaged data.  The host enqueues every copy BEFORE the launch and orders the launch after the
+// first chunk (lm_batched.cu), so a launch that blocks the host (CUDA_LAUNCH_BLOCKING, profilers) cannot starve the
+// copies; the wait is still bounded (`spin_limit` polls of ~1 us) in case the copy engine cannot run beside the kernel
+// at all.  On time-out the flag is raised, every later waiter fails at once, and the host -- which always reads the
+// flag back -- discards the launch and re-runs it unstaged: a time-out never surfaces as per-problem results.
+__device__ __forceinline__ bool wait_staged(const unsigned int* ready, unsigned int idx, unsigned int spin_limit)
 {
     if (!ready) return true;
     unsigned spins = 0;
     for (;;) {
-        unsigned int v;
+        unsigned int v, bad;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
         if (v > idx) return true;
-        if (++spins > 20000000u) return false;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(bad) : "l"(ready + 1) : "memory");
+        if (bad || ++spins > spin_limit) {
+            if (!bad) atomicExch(const_cast<unsigned int*>(ready) + 1, 1u);
+            return false;
+        }
         __nanosleep(1000);
     }
 }
@@ -75,13 +82,22 @@ __device__ __forceinline__ bool wait_staged(const unsigned int* ready, unsigned 
 // mu *= 2 (LS:1125-1130).  Nothing else changes (age == 0, so `mu > 16` cannot force a new Jacobian, LS:984-989),
 // |q| / lambda only shrinks, and the same holds for every later pass until !(lambda <= maxLambda) ends the run with
 // furtherImprovement (LS:979-983).  The caller therefore replays only the scalar recurrence (fCalls, lambda, mu).
-template <class T, int N>
-__device__ __forceinline__ bool tail_is_inert(const T (&x)[N], const T (&Jy)[N], T lambda)
+// Two more conditions make the replay exact in the corners: (1) no x_i may sit ON a bound -- with the tiny step pointing
+// outward BOXCQP would enter its active-set loop (BQ:243-254), which also snaps any other x_j within the QP tolerance of
+// its bound, so the trial point could differ from x; with every x_i strictly inside, x_i - l_i >= ulp(x_i)/2 > |d_i| and
+// the unconstrained solution is returned at BQ:216-219; (2) maxStep must be positive, otherwise LS:1101-1106 rejects
+// BEFORE the evaluation is counted (fCalls would differ).
+template <class T, int N, class BL, class BU>
+__device__ __forceinline__ bool tail_is_inert(const T (&x)[N], const T (&Jy)[N], T lambda, const BL& lo, const BU& up, T maxStep)
 {
     T q2 = (T)0, xmin = Num<T>::inf();
 #pragma unroll
     for (int i = 0; i < N; ++i) { q2 += Jy[i] * Jy[i]; xmin = t_min(xmin, t_abs(x[i])); }
-    return xmin > (T)0 && sqrt_ni(q2) < lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125));
+    if (!(xmin > (T)0 && maxStep > (T)0 && sqrt_ni(q2) < lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125)))) return false;
+    bool inside = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) inside = inside && (lo[i] < x[i]) && (x[i] < up[i]);
+    return inside;
 }
 
 template <class Model, class T, int LANES, int R, bool FD>
@@ -120,14 +136,14 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
         unsigned int staged = 1;
         if (glane == 0) {
             prob32 = atomicAdd(args.counter, 1u);
-            if (prob32 < args.batch) staged = wait_staged(args.ready, prob32) ? 1u : 0u;
+            if (prob32 < args.batch) staged = wait_staged(args.ready, prob32, args.spin_limit) ? 1u : 0u;
         }
         prob32 = __shfl_sync(gmask, prob32, 0, LANES);
         staged = __shfl_sync(gmask, staged, 0, LANES);
         if (prob32 >= args.batch) break;
         const unsigned long long prob = prob32;
         ++sProblems;
-        if (!staged) {                                  // inputs never arrived (host-side copy failed): fail loudly, do not touch x
+        if (!staged) {                                  // inputs never arrived: the host discards this launch (flag ready[1]); do not touch x
             if (glane == 0) {
                 Result bad;
                 bad.status = mir_ls_numericError; bad.iterations = 0; bad.fCalls = 0; bad.gCalls = 0; bad.residual = Num<T>::inf(); bad.lambda = (T)0;
@@ -345,7 +361,7 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                     }
                 }
 
-                if (age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, lambda)) {
+                if (age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, lambda, lo, up, st.maxStep)) {
                     // (needJacobian is false here.)  Replay the rejections: LS:1112, 1125-1130, then the next pass's LS:979-983.
                     for (;;) {
                         ++ret.fCalls;

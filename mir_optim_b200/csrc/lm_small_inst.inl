@@ -15,7 +15,10 @@ int launch_small_model<REAL>(unsigned model, size_t n, const Num<REAL>::Settings
         set_error("mir_optim_b200: model expects n = " + std::to_string(want) + ", got " + std::to_string(n));
         return (int)MIR_B200_EINVAL;
     };
-    if (use_thread_per_problem(args.batch)) {
+    // m beyond the largest rows-per-lane instantiation of the lane-group kernel (4 x 32 rows): the thread-per-problem
+    // kernel takes any m, whatever the batch size (a single problem is left to the caller: the legacy entry point
+    // sends it to the row-parallel large-problem engine instead of one thread)
+    if (use_thread_per_problem(args.batch) || (args.m > 128 && args.batch > 1)) {
         switch (model) {
         case MIR_MODEL_EXPDECAY2:  if (n != 2) return bad_n(2); return launch_tpp<ModelExpDecay2<T, true>, T>(st, args, stream);
         case MIR_MODEL_EXPTAU3:    if (n != 3) return bad_n(3); return launch_tpp<ModelExpTau3<T, true>, T>(st, args, stream);

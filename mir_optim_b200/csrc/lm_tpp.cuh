@@ -164,8 +164,8 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
         if (!active && !retired) {
             const unsigned int idx = atomicAdd(args.counter, 1u);
             if (idx >= args.batch) retired = true;
-            else if (!wait_staged(args.ready, idx)) {
-                // inputs never arrived (host-side copy failed): fail loudly, do not touch x
+            else if (!wait_staged(args.ready, idx, args.spin_limit)) {
+                // inputs never arrived: the host discards this launch (flag ready[1]); do not touch x
                 Result ret;
                 ret.status = mir_ls_numericError; ret.iterations = 0; ret.fCalls = 0; ret.gCalls = 0; ret.residual = Num<T>::inf(); ret.lambda = (T)0;
                 static_cast<Result*>(args.results)[idx] = ret;
@@ -244,7 +244,7 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
 #pragma unroll
                     for (int i = 0; i < N; ++i) nan = nan || !(x[i] <= x[i]);
                     if (nan) { status = mir_ls_numericError; finished = true; }
-                    else if (!needJacobian && age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, lambda)) {
+                    else if (!needJacobian && age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, lambda, lp, upp, st.maxStep)) {
                         for (;;) {                         // replay LS:1112, 1125-1130 and the next pass's LS:979-983
                             ++fCalls;
                             lambda *= st.lambdaIncrease * mu; mu *= (T)2;

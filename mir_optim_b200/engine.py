@@ -152,6 +152,17 @@ class Engine(ReferenceAPI):
                                                                       _vp(iterations), C.c_void_p(stream))
         self._check(rc)
 
+    def posvx_batched(self, A: np.ndarray, b: np.ndarray, variant: int, device: int = -1):
+        """Diagnostics: the device restatement of LAPACK ?posvx('E','L') alone.  A (batch, n, n) row-major (lower triangle
+        read), b (batch, n).  Returns (x, info int32[batch], equed int32[batch]).  variant: see the header."""
+        sfx = _types(A.dtype)[0]
+        batch, n = b.shape
+        assert A.shape == (batch, n, n) and A.flags.c_contiguous and b.flags.c_contiguous and b.dtype == A.dtype
+        x = np.zeros((batch, n), dtype=A.dtype)
+        info = np.full(batch, -1, dtype=np.int32); equed = np.full(batch, -1, dtype=np.int32)
+        self._check(getattr(self.lib, f"mir_b200_posvx_batched_{sfx}")(variant, batch, n, _vp(A), _vp(b), _vp(x), _vp(info), _vp(equed), device))
+        return x, info, equed
+
     # -- one problem through the reference's own entry point, residual model on the device ------
     def optimize_device_model(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
                               t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,

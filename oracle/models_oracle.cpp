@@ -70,7 +70,10 @@ void model_f(void* vctx, size_t m, size_t n, const T* p, T* r)
         }
         break;
     case MIR_MODEL_GAUSSMIX:
-        for (size_t i = 0; i < m; ++i) {
+        // (rows are independent: the OpenMP loop gives the same bits for any thread count; it only matters for the
+        //  single large problem of configs[3], where the CPU baseline is meant to use all host cores)
+#pragma omp parallel for schedule(static) if (m >= 65536)
+        for (long long i = 0; i < (long long)m; ++i) {
             T acc = p[n - 2] + p[n - 1] * t[i];
             for (size_t k = 0; k + 3 <= n - 2; k += 3) {
                 T z = (t[i] - p[k + 1]) * (1 / p[k + 2]);
@@ -132,7 +135,8 @@ void model_g(void* vctx, size_t m, size_t n, const T* p, T* J)
             }
         break;
     case MIR_MODEL_GAUSSMIX:
-        for (size_t i = 0; i < m; ++i) {
+#pragma omp parallel for schedule(static) if (m >= 65536)
+        for (long long i = 0; i < (long long)m; ++i) {
             for (size_t k = 0; k + 3 <= n - 2; k += 3) {
                 T is = 1 / p[k + 2];
                 T z = (t[i] - p[k + 1]) * is;
@@ -177,6 +181,7 @@ int batched(const typename API<T>::S* settings, const mir_model_desc* model, siz
 #else
     nthreads = 1;
 #endif
+    if ((size_t)nthreads > batch) nthreads = (int)(batch ? batch : 1);   // one problem: leave the threads to OpenBLAS and the row loops
 #pragma omp parallel num_threads(nthreads)
     {
         std::vector<T> work(wl + 8);

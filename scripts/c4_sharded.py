@@ -15,6 +15,7 @@ ap.add_argument("--K", type=int, default=42)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--max-iterations", type=int, default=0)
 ap.add_argument("--noise", type=float, default=1e-3)
+ap.add_argument("--robust", action="store_true", help="robust termination: maxGoodResidual = 4 m noise^2 => fConverged (SURVEY 8c P3)")
 ap.add_argument("--no-comm", action="store_true", help="each rank solves its own rows independently (diagnostic)")
 ap.add_argument("--own-stream", action="store_true")
 a = ap.parse_args()
@@ -33,6 +34,8 @@ t = torch.from_numpy(wl.t).cuda(); y = torch.from_numpy(wl.y).cuda()
 s = eng.settings()
 if a.max_iterations:
     s.maxIterations = a.max_iterations
+if a.robust:
+    s.maxGoodResidual = 4.0 * a.m * a.noise * a.noise
 out = None
 side = torch.cuda.Stream() if a.own_stream else None
 for rep in range(a.reps):

@@ -98,6 +98,32 @@ def oracle_batched_mp(lib, settings, model, x0, l, u, t=None, y=None, m=None, fd
     return x, res, procs
 
 
+def _mp_qp_worker(span):
+    lo, hi = span
+    a = _MP
+    x, st, it = oracle_box_qp_batched(a["lib"], a["P"][lo:hi], a["q"][lo:hi], a["l"][lo:hi], a["u"][lo:hi], a["settings"], nthreads=1)
+    return lo, x, st, it
+
+
+def oracle_box_qp_batched_mp(lib, P, q, l, u, settings=None, procs=0):
+    """oracle_box_qp_batched over forked processes (0 = all cores), one single-threaded OpenBLAS each."""
+    import multiprocessing as mp
+    import os
+    procs = procs or (os.cpu_count() or 1)
+    batch = len(q)
+    if procs <= 1 or batch < 4 * procs:
+        return oracle_box_qp_batched(lib, P, q, l, u, settings, nthreads=1) + (1,)
+    _MP.update(lib=lib, settings=settings, P=P, q=q, l=l, u=u)
+    chunk = max(1, min(256, (batch + 4 * procs - 1) // (4 * procs)))
+    spans = [(s, min(batch, s + chunk)) for s in range(0, batch, chunk)]
+    x = np.empty_like(q); st = np.empty(batch, dtype=np.int32); it = np.empty(batch, dtype=np.uint32)
+    with mp.get_context("fork").Pool(procs) as pool:
+        for lo, xs, ss, its in pool.imap_unordered(_mp_qp_worker, spans):
+            x[lo:lo + len(xs)] = xs; st[lo:lo + len(ss)] = ss; it[lo:lo + len(its)] = its
+    _MP.clear()
+    return x, st, it, procs
+
+
 def self_sensitivity(lib, settings, wl, dtype=np.float64, fd=None, seed=99):
     """The reference algorithm's own conditioning: run the oracle on the workload and on a copy whose samples are
     each moved by ONE ulp (up or down at random) -- rounding-level input noise, which is what a different

@@ -86,6 +86,32 @@ def test_c4_gaussmix_trajectory_and_low_noise_fit(eng, oracle_lib, K, m, fd):
     np.testing.assert_allclose(x, wl.truth[0], rtol=2e-2, atol=1e-4)
 
 
+def test_c4_full_size_against_oracle(eng, oracle_lib):
+    """configs[3] at the BASELINE size, m = 4,000,000, n = 128, against the oracle (OpenBLAS on all host cores, ~8 s per LM
+    pass on 8 cores): k-step trajectories and one robust-termination solve.  J alone is 4.1 GB on either side."""
+    import os
+    from mir_optim_b200 import workloads
+    m = 4_000_000
+    oracle_lib.oracle_set_blas_threads(os.cpu_count() or 1)
+    try:
+        wl = workloads.c4_gaussmix(m=m, noise=1e-3)
+        for k in (1, 3):
+            s = eng.settings(); s.maxIterations = k
+            x, r, xo, ro = _solve_both(eng, oracle_lib, wl, s, False)
+            assert (r.status, r.iterations, r.fCalls, r.gCalls) == (ro["status"], ro["iterations"], ro["fCalls"], ro["gCalls"]), (k, r, ro)
+            assert np.max(rel_err(x, xo)) < 1e-9, (k, np.max(rel_err(x, xo)))
+            assert abs(r.residual - ro["residual"]) <= 1e-9 * ro["residual"], k
+            assert r.lambda_ == pytest.approx(ro["lambda"], rel=1e-9)
+        wl = workloads.c4_gaussmix(m=m, noise=1e-6)
+        s = eng.settings(); s.maxGoodResidual = 4.0 * m * 1e-12
+        x, r, xo, ro = _solve_both(eng, oracle_lib, wl, s, False)
+        assert r.status == ro["status"] == 3 and r.iterations == ro["iterations"]
+        assert np.max(rel_err(x, xo)) < 1e-8
+        np.testing.assert_allclose(x, wl.truth[0], rtol=2e-2, atol=1e-4)
+    finally:
+        oracle_lib.oracle_set_blas_threads(1)
+
+
 def test_c4_sharded_entry_single_gpu_with_bounds(eng, oracle_lib):
     """mir_optimize_least_squares_sharded_d with comm = NULL (one rank), box bounds active at the solution."""
     import torch
