@@ -91,9 +91,36 @@ template <class T> __device__ void large_begin_pass(LargeCtl<T>* c)
         // inert lambda-overflow tail (proof at tail_is_inert in lm_small.cuh): replay the scalar recurrence only
         T q2 = (T)0, xmin = Num<T>::inf();
         for (int i = 0; i < c->n; ++i) { q2 += c->Jy[i] * c->Jy[i]; xmin = t_min(xmin, t_abs(c->x[i])); }
-        bool inside = c->st.maxStep > (T)0;           // + no x_i on a bound, + LS:1101 cannot pre-empt the evaluation (see tail_is_inert)
-        for (int i = 0; i < c->n; ++i) inside = inside && (c->l[i] < c->x[i]) && (c->x[i] < c->u[i]);
-        if (inside && xmin > (T)0 && sqrt_ni(q2) < c->lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125))) {
+        // + maxStep > 0, and BOXCQP must provably return `solved`: no x_i on a bound, or the on-bound certificate
+        // (tail_bounds_certificate in lm_small.cuh, same conditions, restated here for run-time n)
+        bool ok = c->st.maxStep > (T)0 && xmin > (T)0 && sqrt_ni(q2) < c->lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125));
+        bool any = false;
+        for (int i = 0; ok && i < c->n; ++i) {
+            ok = (c->l[i] <= c->x[i]) && (c->x[i] <= c->u[i]);
+            any = any || (c->l[i] == c->x[i]) || (c->u[i] == c->x[i]);
+        }
+        if (ok && any) {
+            const int n = c->n;
+            T nu = (T)0, qinf = (T)0;
+            for (int i = 0; i < n; ++i) {
+                T row = (T)0;
+                for (int j = 0; j < n; ++j) row += t_abs(c->JJ[trisym(i, j)]);
+                nu = t_max(nu, row); qinf = t_max(qinf, t_abs(c->Jy[i]));
+            }
+            ok = c->lambda >= (T)4 * nu;
+            const T thr = ((T)8 * nu) * (qinf / c->lambda), dmax = xmin * (Num<T>::lapack_eps() * (T)0.25);
+            const T relTol = c->st.qpSettings.relTolerance, absTol = c->st.qpSettings.absTolerance;
+            for (int i = 0; ok && i < n; ++i) {
+                const T ql = c->l[i] - c->x[i], qu = c->u[i] - c->x[i];
+                const bool onL = ql == (T)0, onU = qu == (T)0;
+                const bool farL = (-ql - dmax) >= (T)2 * (relTol + absTol * t_abs(ql));
+                const bool farU = (qu - dmax) >= (T)2 * (relTol + absTol * t_abs(qu));
+                if (onL && onU) ok = false;
+                else if (onL || onU) ok = (onL ? farU : farL) && (t_abs(c->Jy[i]) >= thr);
+                else ok = farL && farU;
+            }
+        }
+        if (ok) {
             for (;;) {
                 ++c->fCalls;
                 c->lambda *= c->st.lambdaIncrease * c->mu; c->mu *= (T)2;

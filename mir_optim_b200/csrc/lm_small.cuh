@@ -82,22 +82,75 @@ __device__ __forceinline__ bool wait_staged(const unsigned int* ready, unsigned 
 // mu *= 2 (LS:1125-1130).  Nothing else changes (age == 0, so `mu > 16` cannot force a new Jacobian, LS:984-989),
 // |q| / lambda only shrinks, and the same holds for every later pass until !(lambda <= maxLambda) ends the run with
 // furtherImprovement (LS:979-983).  The caller therefore replays only the scalar recurrence (fCalls, lambda, mu).
-// Two more conditions make the replay exact in the corners: (1) no x_i may sit ON a bound -- with the tiny step pointing
-// outward BOXCQP would enter its active-set loop (BQ:243-254), which also snaps any other x_j within the QP tolerance of
-// its bound, so the trial point could differ from x; with every x_i strictly inside, x_i - l_i >= ulp(x_i)/2 > |d_i| and
-// the unconstrained solution is returned at BQ:216-219; (2) maxStep must be positive, otherwise LS:1101-1106 rejects
-// BEFORE the evaluation is counted (fCalls would differ).
+// Two more conditions make the replay exact in the corners: maxStep must be positive (otherwise LS:1101-1106 rejects BEFORE
+// the evaluation is counted and fCalls would differ), and the step must provably come back from BOXCQP as `solved`:
+//  * No x_i on a bound: x_i - l_i >= ulp(x_i)/2 > |d_i|, the unconstrained solution passes the first test (BQ:216-219,
+//    no tolerance involved) and is returned.
+//  * Some x_i ON a bound (qpl_i == 0 or qpu_i == 0; ~10 % of BASELINE configs[1] end like this): the active-set loop may
+//    run, and the certificate below (tail_bounds_certificate) shows it returns `solved` with a step that still vanishes.
+//    Let nu = ||JJ||_inf and lambda >= 4 nu.  For ANY free set f the sub-solution is d_f = -(lambda I + JJ_ff)^-1 q_f =
+//    -(q_f + e)/lambda with |e|_inf <= (4 nu / 3 lambda) |q|_inf, so |d|_inf <= 1.34 |q|_inf / lambda (tiny: the bound used
+//    above) and, for every on-bound i with |q_i| >= 8 nu |q|_inf / lambda, sign(d_i) = -sign(q_i) and the multiplier
+//    (P d + q)_i = q_i + sum_f JJ_if d_f has the sign of q_i.  Variables off their bounds keep a margin of more than the
+//    QP tolerance plus |d| on both sides, so BQ:239-263 never flags them.  Trace of BQ:234-375: the first test fails only if
+//    some on-bound variable points outward; iteration 1 flags those (xl < 0) and possibly inward ones (xl < tol with a zero
+//    multiplier); outward ones get multipliers of the right sign and stay flagged (xl = 0 < tol, la >= 0), inward ones get
+//    a negative multiplier, are released in iteration 2 (mu = la = 0, d_i > 0 inside) and the tests at BQ:339-347 pass:
+//    `solved` after at most two iterations, never the all-free exit (BQ:265-266: an outward variable stays flagged).
+//    Every condition only gets easier as lambda grows, so it holds for all later passes of the tail.
+template <class T, int N> struct TailCase {
+    T x[N], q[N], lo[N], up[N], JJ[N * (N + 1) / 2];
+    T lambda, dmax, relTol, absTol;
+};
+template <class T, int N>
+__device__ __noinline__ bool tail_bounds_certificate(const TailCase<T, N> c)
+{
+    bool any = false;
+    for (int i = 0; i < N; ++i) any = any || (c.lo[i] == c.x[i]) || (c.up[i] == c.x[i]);
+    if (!any) return true;                                 // (the caller has checked lo < x < up otherwise)
+    T nu = (T)0, qinf = (T)0;
+    for (int i = 0; i < N; ++i) {
+        T row = (T)0;
+        for (int j = 0; j < N; ++j) row += t_abs(c.JJ[trisym(i, j)]);
+        nu = t_max(nu, row); qinf = t_max(qinf, t_abs(c.q[i]));
+    }
+    if (!(c.lambda >= (T)4 * nu)) return false;
+    const T thr = ((T)8 * nu) * (qinf / c.lambda);
+    for (int i = 0; i < N; ++i) {
+        const T ql = c.lo[i] - c.x[i], qu = c.up[i] - c.x[i];                       // LS:1074-1077
+        const bool onL = ql == (T)0, onU = qu == (T)0;
+        const bool farL = (-ql - c.dmax) >= (T)2 * (c.relTol + c.absTol * t_abs(ql));   // an infinite bound is far (inf >= inf)
+        const bool farU = (qu - c.dmax) >= (T)2 * (c.relTol + c.absTol * t_abs(qu));
+        if (onL && onU) return false;
+        if (onL || onU) {
+            if (!(onL ? farU : farL)) return false;
+            if (!(t_abs(c.q[i]) >= thr)) return false;
+        } else if (!(farL && farU)) return false;
+    }
+    return true;
+}
+
 template <class T, int N, class BL, class BU>
-__device__ __forceinline__ bool tail_is_inert(const T (&x)[N], const T (&Jy)[N], T lambda, const BL& lo, const BU& up, T maxStep)
+__device__ __forceinline__ bool tail_is_inert(const T (&x)[N], const T (&Jy)[N], const T (&JJ)[N * (N + 1) / 2], T lambda, const BL& lo, const BU& up,
+                                              const typename Num<T>::Settings& st)
 {
     T q2 = (T)0, xmin = Num<T>::inf();
 #pragma unroll
     for (int i = 0; i < N; ++i) { q2 += Jy[i] * Jy[i]; xmin = t_min(xmin, t_abs(x[i])); }
-    if (!(xmin > (T)0 && maxStep > (T)0 && sqrt_ni(q2) < lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125)))) return false;
-    bool inside = true;
+    if (!(xmin > (T)0 && st.maxStep > (T)0 && sqrt_ni(q2) < lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125)))) return false;
+    bool inside = true, strict = true;
 #pragma unroll
-    for (int i = 0; i < N; ++i) inside = inside && (lo[i] < x[i]) && (x[i] < up[i]);
-    return inside;
+    for (int i = 0; i < N; ++i) { inside = inside && (lo[i] <= x[i]) && (x[i] <= up[i]); strict = strict && (lo[i] < x[i]) && (x[i] < up[i]); }
+    if (strict) return true;
+    if (!inside) return false;
+    TailCase<T, N> c;                                      // rare path, out of line: the caller's registers stay untouched
+#pragma unroll
+    for (int i = 0; i < N; ++i) { c.x[i] = x[i]; c.q[i] = Jy[i]; c.lo[i] = lo[i]; c.up[i] = up[i]; }
+#pragma unroll
+    for (int i = 0; i < N * (N + 1) / 2; ++i) c.JJ[i] = JJ[i];
+    c.lambda = lambda; c.dmax = xmin * (Num<T>::lapack_eps() * (T)0.25);
+    c.relTol = st.qpSettings.relTolerance; c.absTol = st.qpSettings.absTolerance;
+    return tail_bounds_certificate<T, N>(c);
 }
 
 template <class Model, class T, int LANES, int R, bool FD>
@@ -361,7 +414,7 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                     }
                 }
 
-                if (age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, lambda, lo, up, st.maxStep)) {
+                if (age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, JJ, lambda, lo, up, st)) {
                     // (needJacobian is false here.)  Replay the rejections: LS:1112, 1125-1130, then the next pass's LS:979-983.
                     for (;;) {
                         ++ret.fCalls;

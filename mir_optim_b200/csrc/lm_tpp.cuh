@@ -244,7 +244,7 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
 #pragma unroll
                     for (int i = 0; i < N; ++i) nan = nan || !(x[i] <= x[i]);
                     if (nan) { status = mir_ls_numericError; finished = true; }
-                    else if (!needJacobian && age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, lambda, lp, upp, st.maxStep)) {
+                    else if (!needJacobian && age == 0 && tailShortcut && tail_is_inert<T, N>(x, Jy, JJ, lambda, lp, upp, st)) {
                         for (;;) {                         // replay LS:1112, 1125-1130 and the next pass's LS:979-983
                             ++fCalls;
                             lambda *= st.lambdaIncrease * mu; mu *= (T)2;
