@@ -47,7 +47,12 @@ int launch_small_model<REAL>(unsigned model, size_t n, const Num<REAL>::Settings
         return launch_small<ModelGauss4<T>, T, 32, 4>(st, args, stream);
     case MIR_MODEL_SUMEXP:
         if (n == 4) return launch_small<ModelSumExp<T, 4>, T, 32, 2, 4>(st, args, stream);
-        if (n == 8) return launch_small<ModelSumExp<T, 8>, T, 32, 2, 4>(st, args, stream);
+        if (n == 8) {
+            // four problems per warp (lm_mux.cuh); MIRB200_N8_KERNEL=warp keeps the one-warp-per-problem kernel (experiments)
+            static const bool warpKernel = [] { const char* e = std::getenv("MIRB200_N8_KERNEL"); return e && !std::strcmp(e, "warp"); }();
+            if (args.m <= (unsigned)MUX_MMAX && !warpKernel) return launch_mux<ModelSumExp<T, 8, true>, T>(st, args, stream);
+            return launch_small<ModelSumExp<T, 8>, T, 32, 2, 4>(st, args, stream);
+        }
         set_error("mir_optim_b200: batched SUMEXP is instantiated for n = 4 and n = 8");
         return MIR_B200_EUNSUPPORTED;
     default:

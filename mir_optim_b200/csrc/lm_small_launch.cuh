@@ -5,6 +5,7 @@
 #include <cstring>
 #include "lm_small.cuh"
 #include "lm_tpp.cuh"
+#include "lm_mux.cuh"
 #include "runtime.cuh"
 
 namespace mirb200 {
@@ -75,6 +76,30 @@ template <class Model, class T>
 int launch_tpp(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
     return (args.flags & MIR_MODEL_FD_JACOBIAN) ? launch_tpp_fd<Model, T, true>(st, args, stream) : launch_tpp_fd<Model, T, false>(st, args, stream);
+}
+
+// Four problems per warp (lm_mux.cuh): n <= 8, m <= 128.
+template <class Model, class T, bool FD>
+int launch_mux_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    auto kern = lm_mux_kernel<Model, T, FD>;
+    const size_t smem = sizeof(MuxWarpSmem<T>) * MUX_WARPS;
+    MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocksPerSM = 0;
+    MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, MUX_WARPS * 32, smem));
+    if (blocksPerSM < 1) blocksPerSM = 1;
+    const unsigned long long perBlock = (unsigned long long)MUX_WARPS * MUX_SLOTS;
+    unsigned long long blocksWanted = (args.batch + perBlock - 1) / perBlock;
+    unsigned long long grid = (unsigned long long)sm_count() * blocksPerSM;      // persistent: one resident wave
+    if (blocksWanted < grid) grid = blocksWanted ? blocksWanted : 1;
+    kern<<<(unsigned)grid, MUX_WARPS * 32, smem, stream>>>(st, args);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "lm_mux_kernel launch");
+}
+template <class Model, class T>
+int launch_mux(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    return (args.flags & MIR_MODEL_FD_JACOBIAN) ? launch_mux_fd<Model, T, true>(st, args, stream) : launch_mux_fd<Model, T, false>(st, args, stream);
 }
 
 // Kernel choice: one thread per problem once the batch can fill the GPU with threads, else one lane group per

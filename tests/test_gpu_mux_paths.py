@@ -1,0 +1,153 @@
+"""GPU parity of the four-problems-per-warp LM kernel (lm_mux.cuh) -- the kernel behind BASELINE configs[2], 8-parameter
+sums of exponentials -- against the CPU oracle, beyond what tests/test_gpu_batched_parity.py already sends through it
+(configs[2] with finite differences: k-step trajectories, noise-free robust termination, realistic noise, tail replay):
+
+  * analytic Jacobian (maxAge = 3 default and others): Broyden ageing between fresh Jacobians
+  * box bounds that are active at the solution: the distributed BOXCQP active-set loop (BQ:234-375) and its multipliers
+  * row counts that are not a multiple of 32, fewer rows than lanes, per-problem abscissae and bounds
+  * argument validation statuses, a batch that is not a multiple of the four slots of a warp
+  * the distributed ?posvx against the warp-per-problem kernel's register-resident one (same trajectories)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from mir_optim_b200 import workloads
+from mir_optim_b200._abi import LeastSquaresStatus as S
+from oracle_util import oracle_batched_mp, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import mir_optim_b200
+    assert mir_optim_b200.engine.device_count() > 0, "no CUDA device"
+    return mir_optim_b200.engine
+
+
+def sumexp8(batch, m, seed, noise=0.01, dtype=np.float64):
+    return workloads.c3_sumexp8(batch, dtype=dtype, seed=seed, m=m, noise=noise)
+
+
+def both(eng, oracle_lib, wl, mut, fd, l=None, u=None, t=None, dtype=np.float64):
+    sg = eng.settings(dtype); so = eng.settings(dtype)
+    mut(sg); mut(so)
+    l = wl.l if l is None else l; u = wl.u if u is None else u; t = wl.t if t is None else t
+    xg = wl.x0.copy()
+    rg, stats = eng.optimize_batched(sg, wl.model, xg, l, u, t=t, y=wl.y, fd_jacobian=fd, want_stats=True)
+    xo, ro, _ = oracle_batched_mp(oracle_lib, so, wl.model, wl.x0, l, u, t=t, y=wl.y, fd_jacobian=fd)
+    return xg, rg, xo, ro, stats
+
+
+def same_counters(rg, ro):
+    return ((rg["status"] == ro["status"]) & (rg["iterations"] == ro["iterations"]) & (rg["fCalls"] == ro["fCalls"])
+            & (rg["gCalls"] == ro["gCalls"]))
+
+
+@pytest.mark.parametrize("max_age,fd,m", [(0, False, 128), (1, False, 128), (5, False, 100), (0, True, 100), (3, True, 17), (0, False, 33)])
+def test_k_step_trajectories_n8(eng, oracle_lib, max_age, fd, m):
+    wl = sumexp8(1003, m, seed=21)                 # 1003: not a multiple of the 4 slots of a warp
+    for k in (1, 2, 3, 5):
+        def mut(s, k=k):
+            s.maxIterations = k
+            s.maxAge = max_age
+        xg, rg, xo, ro, stats = both(eng, oracle_lib, wl, mut, fd)
+        same = same_counters(rg, ro)
+        assert same.mean() >= (1.0 if k <= 3 else 0.99), (k, max_age, fd, m, float(same.mean()))
+        # (m = 17 rows for 8 parameters is nearly under-determined: rounding differences grow faster along the trajectory)
+        tol = (1e-9 if fd else 1e-11) * (1 if k <= 3 else (20 if m >= 32 else 500))
+        ex = np.max(rel_err(xg[same], xo[same])); er = np.max(rel_err(rg["residual"][same], ro["residual"][same]))
+        el = rel_err(rg["lambda"][same], ro["lambda"][same])
+        assert ex < tol and er < tol * 20, (k, max_age, fd, m, ex, er)
+        assert (el.max() < 1e-12) if k <= 3 else (np.mean(el > 1e-12) < 0.01), (k, float(el.max()))
+        assert stats["problems"] == 1003
+
+
+def test_active_bounds_n8(eng, oracle_lib):
+    """Bounds that cut off the true amplitudes / rates of some components: the solution sits on several bounds, every pass
+    runs the active-set loop of the distributed BOXCQP."""
+    wl = sumexp8(1024, 128, seed=22)
+    rng = np.random.default_rng(5)
+    l = np.tile(np.array([0.0, 0.0] * 4), (1024, 1)); u = np.tile(np.array([6.0, 12.0] * 4), (1024, 1))
+    u[:, 0] = wl.truth[:, 0] * rng.uniform(0.7, 0.95, 1024)          # amplitude of component 0 capped below its true value
+    l[:, 3] = wl.truth[:, 3] * rng.uniform(1.05, 1.3, 1024)          # rate of component 1 forced above its true value
+    wl["x0"] = np.clip(wl.x0, l, u)
+    for k in (1, 2, 3):
+        def mut(s, k=k): s.maxIterations = k
+        for fd in (True, False):
+            xg, rg, xo, ro, stats = both(eng, oracle_lib, wl, mut, fd, l=l, u=u)
+            same = same_counters(rg, ro)
+            assert same.mean() >= 0.995, (k, fd, float(same.mean()))
+            assert np.max(rel_err(xg[same], xo[same])) < (1e-8 if fd else 1e-10), (k, fd)
+            assert np.all(xg >= l) and np.all(xg <= u)
+            assert stats["qp_iterations"] > 0
+
+    def mut(s): pass
+    xg, rg, xo, ro, stats = both(eng, oracle_lib, wl, mut, False, l=l, u=u)
+    assert np.all(rg["status"] >= -1)
+    onb_g = (xg == l) | (xg == u); onb_o = (xo == l) | (xo == u)
+    assert onb_o.any(axis=1).mean() > 0.9
+    assert np.mean(np.all(onb_g == onb_o, axis=1)) > 0.97                      # same active set at the solution
+    er = rel_err(rg["residual"], ro["residual"])
+    assert np.quantile(er, 0.95) < 1e-8
+
+
+def test_per_problem_grids_and_validation_n8(eng, oracle_lib):
+    wl = sumexp8(515, 96, seed=23)
+    rng = np.random.default_rng(9)
+    t2 = np.ascontiguousarray(wl.t[None, :] * rng.uniform(0.95, 1.05, (515, 1)))
+    x0 = wl.x0.copy()
+    x0[3, 2] = np.nan; x0[100, 7] = np.inf                       # badGuess
+    l = np.tile(wl.l, (515, 1)); u = np.tile(wl.u, (515, 1))
+    u[200, 1] = x0[200, 1] - 1.0                                  # badBounds
+    l[300, 5] = np.nan                                            # badBounds (NaN bound)
+    wl["x0"] = x0
+
+    def mut(s): s.maxIterations = 3
+    xg, rg, xo, ro, _ = both(eng, oracle_lib, wl, mut, True, l=l, u=u, t=t2)
+    assert [rg["status"][i] for i in (3, 100, 200, 300)] == [S.badGuess, S.badGuess, S.badBounds, S.badBounds]
+    assert np.array_equal(rg["status"], ro["status"])
+    for b in (3, 100, 200, 300):
+        assert np.array_equal(xg[b], x0[b], equal_nan=True) and rg["iterations"][b] == 0 and np.isinf(rg["residual"][b])
+    good = rg["status"] >= -1
+    assert np.array_equal(rg["fCalls"][good], ro["fCalls"][good])
+    assert np.max(rel_err(xg[good], xo[good])) < 1e-9
+    for field, val, st in (("minStepQuality", 1.0, S.badMinStepQuality), ("lambdaIncrease", 0.5, S.badLambdaParams)):
+        s = eng.settings(); setattr(s, field, val)
+        r, _ = eng.optimize_batched(s, wl.model, wl.x0[:64].copy(), wl.l, wl.u, t=wl.t, y=wl.y[:64], fd_jacobian=True)
+        assert np.all(r["status"][np.isfinite(wl.x0[:64]).all(axis=1)] == st), field
+
+
+def test_float_analytic_n8(eng, oracle_lib):
+    wl = sumexp8(1024, 128, seed=24, dtype=np.float32)
+    for k in (1, 2):
+        def mut(s, k=k): s.maxIterations = k
+        xg, rg, xo, ro, _ = both(eng, oracle_lib, wl, mut, False, dtype=np.float32)
+        same = (rg["status"] == ro["status"]) & (rg["iterations"] == ro["iterations"]) & (rg["gCalls"] == ro["gCalls"])
+        assert same.mean() >= 0.97
+        assert np.quantile(rel_err(xg[same], xo[same]), 0.99) < 1e-4
+
+
+def test_mux_and_warp_kernels_agree(eng):
+    """The two n = 8 kernels share nothing but the model functors: trajectories to k = 3 must agree to rounding level
+    (the distributed ?posvx applies the same operations per matrix element; sums over rows are ordered differently)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+            "import mir_optim_b200 as mo; from mir_optim_b200 import workloads\n"
+            "wl = workloads.c3_sumexp8(512, seed=31); s = mo.engine.settings(); s.maxIterations = 3\n"
+            "x = wl.x0.copy(); r, _ = mo.engine.optimize_batched(s, wl.model, x, wl.l, wl.u, t=wl.t, y=wl.y, fd_jacobian=True)\n"
+            "np.save(sys.argv[1], np.concatenate([x.ravel(), r['residual'], r['fCalls'].astype(float), r['lambda']]))\n") % root
+    out = []
+    for kern in ("", "warp"):
+        env = dict(os.environ); env["MIRB200_N8_KERNEL"] = kern
+        path = os.path.join(root, "gpurun_out", f"_mux_cmp_{kern or 'mux'}.npy")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        p = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        out.append(np.load(path)); os.remove(path)
+    a, b = out
+    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) < 1e-9

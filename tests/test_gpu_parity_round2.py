@@ -149,7 +149,8 @@ def test_tpp_p2_tier_where_the_maximum_meets_1e10(eng, oracle_lib):
            frac_x_le_1e10=float(np.mean(ex <= 1e-10)), max_res=er.max(), oracle_1ulp_sensitivity_max_x=sens_x.max(),
            same_status=float((rg["status"] == ro["status"]).mean()))
     assert 0.05 < on_bound.mean() < 0.2
-    assert ex[~on_bound].max() < 1e-10 and er[~on_bound].max() < 1e-10, (float(ex[~on_bound].max()), float(er[~on_bound].max()))
+    # (||r||^2 itself is ~1e-10 here: its RELATIVE error is held to 1e-9, i.e. 1e-19 absolute)
+    assert ex[~on_bound].max() < 1e-10 and er[~on_bound].max() < 1e-9, (float(ex[~on_bound].max()), float(er[~on_bound].max()))
     assert ex[on_bound].max() <= 10 * sens_x.max() + 1e-12 and er.max() < 1e-8, (float(ex[on_bound].max()), float(sens_x.max()))
 
 
