@@ -2,33 +2,38 @@
 // (BASELINE configs[2]: 8-parameter sums of exponentials, finite-difference Jacobian), four problems per warp.
 // Follows optimizeLeastSquaresImplGeneric!T, least_squares.d:877-1176, and solveBoxQP, boxcqp.d:122-379 (cites inline).
 //
-// Why a third batched kernel.  At n = 8 the n-sized part of a pass (the 8 x 8 ?posvx + BOXCQP + lambda control) is as
-// long as the m-sized part.  One warp per problem (lm_small.cuh) runs it 32 times redundantly and needs the packed
-// system, its equilibrated copy and its factor (3 x 36 values) in every lane: 255 registers, 2 KB of spills, 145 KB of
-// code, 0.22 M fits/s (ncu, round 1: 2.9 G local-memory instructions per 65k fits, top stall no_instruction).  One thread
-// per problem (lm_tpp.cuh) has no room for an 8 x 8 system plus an 8-column Jacobian slab either.  Here each phase gets
-// the lane layout that suits it:
+// At n = 8 the n-sized part of a pass (8 x 8 ?posvx + BOXCQP + lambda control) is as long as the m-sized part, one
+// thread cannot hold an 8 x 8 system plus an 8-column Jacobian, and a warp per problem runs the n-sized part 32 times
+// redundantly.  Each phase therefore gets the lane layout that suits it, and ONE WARP (= one CTA) carries four problems
+// ("slots") whose whole state lives in its 44 KB of shared memory:
 //
-//   * ROW phases (residual evaluation, finite-difference / analytic Jacobian, Broyden update LS:999-1006, J^T J and
-//     J^T y, LS:1052, 1065) are WARP-cooperative: all 32 lanes work on ONE of the warp's four problems at a time, lane L
-//     owning rows L, L+32, L+64, L+96.  A warp does exactly the row work its problems ask for -- a problem that needs a
-//     fresh finite-difference Jacobian (16 evaluations) does not hold three others that only need a trial evaluation
-//     in lock step, as sub-warp groups would.  Current / trial residuals and the observations of the four problems
-//     live in registers (3 x 4 x 4 values per lane); the Jacobian lives in shared memory as [slot][parameter][row]
-//     (8 KB per problem in double), conflict-free for both the column writes of the finite differences and the row
-//     reads of the update.
-//   * N-SIZED phases run in four 8-lane GROUPS at once, group g on problem g, lane i owning parameter i: row i of the
+//   * ROW phases (residual evaluation, finite-difference / analytic Jacobian, Broyden update LS:999-1006, J^T y and
+//     J^T J, LS:1052, 1065) are WARP-cooperative: all 32 lanes work on ONE slot at a time, lane L owning rows L, L+32,
+//     L+64, L+96.  A warp does exactly the row work its problems ask for.  Jacobian, current and trial residuals live
+//     in shared memory ([parameter][row], pitch 132: conflict-free for the row accesses, the column writes of the finite
+//     differences and the tensor-core fragment loads); the observations are re-read from global memory (L2) per evaluation.
+//     J^T J runs on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (DMMA) takes J^T (8 x 4 rows) as A and the same values as B,
+//     32 MMAs per 128 rows, the 8 x 8 result arrives distributed over the warp -- no cross-lane reduction of 36 sums.
+//     J^T y rides along on the same fragment loads (one FMA per MMA, two shuffles at the end).
+//   * N-SIZED phases run in four 8-lane GROUPS at once, group g on slot g, lane i owning parameter i: row i of the
 //     system matrix, x_i, its bounds, its multipliers.  The ?posvx restatement is a right-looking Cholesky with one
-//     broadcast per pivot / column element (__shfl_sync inside the group): per matrix element the same operations in
-//     the same order as the dot form of boxqp_small.cuh (element (i,k) takes its updates with pivot j ascending), 8
-//     values of the matrix per lane instead of 108, no spills, and the square roots / reciprocals of the eight pivots
-//     are the only serial chain.  BOXCQP's per-variable logic (flags, multipliers, KBN right-hand side, BQ:239-347) is
-//     naturally lane-parallel; its any / all tests are group votes.
+//     broadcast per pivot / column element; BOXCQP's per-variable logic (flags, multipliers, KBN right-hand side,
+//     BQ:239-347) is lane-parallel, its any / all tests are ballots.  Control flow in these phases is WARP-UNIFORM:
+//     every shuffle / ballot uses the full mask (width 8) and groups that do not take part are predicated off, so the
+//     compiler emits plain SHFL / VOTE instructions instead of a convergence loop per collective.
+//   * All exponentials of the kernel go through ONE inlined exp_repro_many block inside ONE loop ("evaluation items":
+//     initial / trial residuals and the 2n evaluations of a finite-difference Jacobian), and the two row phases of a
+//     pass share one copy of the code (the pass loop is folded in two halves): the kernel is a few thousand
+//     instructions instead of 11,000 (round-2 ncu of the first version: stall_no_instruction 6.7 of 12 cycles per issue).
+//   * Models whose finite-difference evaluations share sub-expressions say so (Model::kFDShared): for a sum of
+//     exponentials, perturbing one parameter changes one term, so the other terms' exps are computed once per Jacobian
+//     instead of 2n times -- the same operations on the same operands, hence the same bits, 12 exps per row instead of 64.
 //
 // Equivalences (bit-exact w.r.t. this file's own arithmetic, as in lm_small.cuh): J^T J is rebuilt only when J changed;
 // a trial point equal to x skips the evaluation (fCalls still counts it); the provably inert lambda-overflow tail is
 // replayed as a scalar recurrence (tail_is_inert, lm_small.cuh -- restated here for the distributed layout).
 #pragma once
+#include <type_traits>
 #include "lm_small.cuh"
 
 namespace mirb200 {
@@ -37,52 +42,86 @@ constexpr int MUX_SLOTS = 4;            // problems per warp
 constexpr int MUX_G = 8;                // lanes per problem in the n-sized phases: n <= 8
 constexpr int MUX_R = 4;                // rows per lane in the row phases (row = lane + 32 k): m <= 128
 constexpr int MUX_MMAX = 32 * MUX_R;
-constexpr int MUX_WARPS = 2;            // warps per CTA (warps never talk to each other)
-constexpr int MUX_RED = 11;             // values per round of the cross-lane reduction (n = 8: 36 + 8 = 4 x 11)
-enum { MUX_JAC_NONE = 0, MUX_JAC_BROYDEN = 1, MUX_JAC_FRESH = 2, MUX_EVAL = 4, MUX_EVAL_INIT = 8 };
+constexpr int MUX_JP = MUX_MMAX + 4;    // pitch of one Jacobian column in shared memory
+constexpr unsigned MUX_FULL = 0xffffffffu;
+// Warps per CTA.  1: every warp is its own CTA and runs free.  > 1: the warps of a CTA (one CTA per SM, as many warps
+// as shared memory holds) step through the phases of the pass loop TOGETHER (a CTA barrier after every phase): they
+// share nothing but the instruction cache, which then holds one phase's code for all of them instead of thrashing
+// between five warps in five different phases.
+// (template parameter MUX_WARPS of the kernel)
+enum { MUX_EVAL_INIT = 1, MUX_EVAL_TRIAL = 2, MUX_JAC_FRESH = 4, MUX_JAC_BROYDEN = 8 };
 
 template <class T> struct MuxWarpSmem {
-    T J[MUX_SLOTS][MUX_G][MUX_MMAX];    // Jacobian of each slot, [parameter][row]
+    T J[MUX_SLOTS][MUX_G][MUX_JP];      // Jacobian of each slot, [parameter][row]; parameters >= n and rows >= m stay zero
+    T vec[MUX_SLOTS][2][MUX_MMAX];      // y (current residuals) and mBuffer (trial / previous residuals); `ysel` says which is which
     T JJ[MUX_SLOTS][MUX_G * MUX_G];     // J^T J, full symmetric storage, undamped
     T Jy[MUX_SLOTS][MUX_G];             // J^T y
-    T red[MUX_RED][33];                 // reduction scratch, one padded row per value
 };
 
-// ---- group (8-lane) collectives; every lane of the group receives the same bits -------------------------------------
-template <class T> __device__ __forceinline__ T gshfl(unsigned gmask, T v, int src) { return __shfl_sync(gmask, v, src, MUX_G); }
-template <class T> __device__ __forceinline__ T gmax8(unsigned gmask, T v)
+// ---- group (8-lane) collectives, executed by the whole warp; every lane of a group receives the same bits -----------
+template <class T> __device__ __forceinline__ T gshfl(T v, int src) { return __shfl_sync(MUX_FULL, v, src, MUX_G); }
+template <class T> __device__ __forceinline__ T gmax8(T v)
 {
 #pragma unroll
-    for (int off = MUX_G / 2; off > 0; off >>= 1) v = t_max(v, __shfl_xor_sync(gmask, v, off, MUX_G));
+    for (int off = MUX_G / 2; off > 0; off >>= 1) v = t_max(v, __shfl_xor_sync(MUX_FULL, v, off, MUX_G));
     return v;
 }
-template <class T> __device__ __forceinline__ T gmin8(unsigned gmask, T v)
+template <class T> __device__ __forceinline__ T gmin8(T v)
 {
 #pragma unroll
-    for (int off = MUX_G / 2; off > 0; off >>= 1) v = t_min(v, __shfl_xor_sync(gmask, v, off, MUX_G));
+    for (int off = MUX_G / 2; off > 0; off >>= 1) v = t_min(v, __shfl_xor_sync(MUX_FULL, v, off, MUX_G));
     return v;
 }
-template <class T> __device__ __forceinline__ T gsum8(unsigned gmask, T v)
+template <class T> __device__ __forceinline__ T gsum8(T v)
 {
 #pragma unroll
-    for (int off = MUX_G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(gmask, v, off, MUX_G);
+    for (int off = MUX_G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(MUX_FULL, v, off, MUX_G);
     return v;
+}
+__device__ __forceinline__ bool gall8(bool p, int gshift) { return ((__ballot_sync(MUX_FULL, p) >> gshift) & 0xffu) == 0xffu; }
+__device__ __forceinline__ bool gany8(bool p, int gshift) { return ((__ballot_sync(MUX_FULL, p) >> gshift) & 0xffu) != 0u; }
+
+__device__ __forceinline__ void mux_dmma884(double (&c)[2], double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// register arrays indexed by a run-time slot: selects / predicated moves instead of local memory
-template <class T> __device__ __forceinline__ T slot_get(const T (&a)[MUX_SLOTS][MUX_R], int s, int k)
+// Pivot step of the Cholesky factorisation: l = sqrt(a) and r = 1 / l (potf2 scales the column by the reciprocal).  The
+// IEEE sqrt followed by the IEEE reciprocal is a chain of ~160 cycles and ~65 instructions; this one starts from the
+// hardware's reciprocal-square-root seed (MUFU.RSQ64H, ~2^-22), runs two Newton steps and corrects l and r once more:
+// both are within an ulp of the rounded values (the restatement is compared with LAPACK by tolerance, not bit for bit).
+__device__ __forceinline__ void mux_sqrt_rcp(double a, double& l, double& r)
 {
-    T r = a[0][k];
-    r = (s == 1) ? a[1][k] : r; r = (s == 2) ? a[2][k] : r; r = (s == 3) ? a[3][k] : r;
-    return r;
+    // (the seed instruction flushes subnormals: tiny pivots are moved up by 2^200 first, an exact scaling; NaN, +-inf
+    //  and pivots <= 0 produce values nobody uses -- the caller has recorded the breakdown, or LAPACK would return NaN too)
+    const bool tiny = a < 0x1p-900;
+    const double as = tiny ? a * 0x1p200 : a;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(as));
+    double t = as * y, e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = as * y; e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    l = as * y;
+    l = fma(fma(-l, l, as), 0.5 * y, l);
+    r = fma(fma(-l, y, 1.0), y, y);
+    l = tiny ? l * 0x1p-100 : l;
+    r = tiny ? r * 0x1p100 : r;
 }
-template <class T> __device__ __forceinline__ void slot_put(T (&a)[MUX_SLOTS][MUX_R], int s, int k, T v)
+__device__ __forceinline__ void mux_sqrt_rcp(float a, float& l, float& r)
 {
-    a[0][k] = (s == 0) ? v : a[0][k]; a[1][k] = (s == 1) ? v : a[1][k];
-    a[2][k] = (s == 2) ? v : a[2][k]; a[3][k] = (s == 3) ? v : a[3][k];
+    const bool tiny = a < 0x1p-100f;
+    const float as = tiny ? a * 0x1p40f : a;
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(as));
+    const float t = as * y, e = fmaf(-t, y, 1.0f);
+    y = fmaf(0.5f * y, e, y);
+    l = as * y;
+    l = fmaf(fmaf(-l, l, as), 0.5f * y, l);
+    r = fmaf(fmaf(-l, y, 1.0f), y, y);
+    l = tiny ? l * 0x1p-20f : l;
+    r = tiny ? r * 0x1p20f : r;
 }
-
-__host__ __device__ constexpr int untri_row(int v) { int i = 0; while ((i + 1) * (i + 2) / 2 <= v) ++i; return i; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // LAPACK ?posvx(FACT='E', UPLO='L') as called at boxcqp.d:194-205 / 310-321, distributed over the 8 lanes of a group:
@@ -91,10 +130,12 @@ __host__ __device__ constexpr int untri_row(int v) { int i = 0; while ((i + 1) *
 // whose bit is clear in `free` (fixed variables of the active set, and lanes >= n) are pinned to the identity, so the
 // free entries see exactly the operands of the compacted system plus exact zeros.
 //   Prow   row gl of P = J^T J + lambda I (all 8 columns, unmasked), Pdiag = Prow[gl]
-// Returns LAPACK info (0, or k > 0: factorisation broke down at pivot k), uniform over the group.
+//   part   this group takes part (the others run along on whatever they hold; their results are ignored)
+// Executed by all 32 lanes in lock step.  Returns LAPACK info (0, or k > 0: factorisation broke down at pivot k),
+// uniform over the group.
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ int posvx_dist(unsigned gmask, int gl, const T (&Prow)[MUX_G], T Pdiag, unsigned free, T b_in, T& x_out)
+__device__ __forceinline__ int posvx_dist(bool part, int gl, const T (&Prow)[MUX_G], T Pdiag, unsigned free, T b_in, T& x_out)
 {
     constexpr int G = MUX_G;
     const bool fi = (free >> gl) & 1u;
@@ -106,22 +147,36 @@ __device__ __forceinline__ int posvx_dist(unsigned gmask, int gl, const T (&Prow
     }
     T b = fi ? b_in : (T)0;
     const T d = fi ? Pdiag : (T)1;
-    // ?poequ over the free rows, ?laqsy decision
-    const T smin = gmin8(gmask, fi ? d : Num<T>::inf());
-    const T amax = gmax8(gmask, fi ? d : -Num<T>::inf());
+    // ?poequ over the free rows, ?laqsy decision: equilibrate iff scond = sqrt(smin) / sqrt(amax) < 0.1 or amax is out of
+    // range.  Single precision settles it unless the ratio is within 10 % of the threshold (or the diagonal leaves the
+    // float range); only then the exact minimum / maximum and the two square roots are computed.
     bool equil = false;
-    if (smin > (T)0) {
-        bool wellScaled;                       // scond = sqrt(smin) / sqrt(amax) >= 0.1; the roots only near the boundary
-        if (smin >= (T)0.0102 * amax) wellScaled = true;
-        else if (smin <= (T)0.0098 * amax) wellScaled = false;
-        else wellScaled = div_ni(sqrt_ni(smin), sqrt_ni(amax)) >= (T)0.1;
-        equil = !(wellScaled && amax >= Num<T>::small_() && amax <= Num<T>::large_());
+    {
+        const float df = (float)d;
+        float fmin_ = fi ? df : __builtin_huge_valf(), fmax_ = fi ? df : 0.0f;
+#pragma unroll
+        for (int off = MUX_G / 2; off > 0; off >>= 1) {
+            fmin_ = fminf(fmin_, __shfl_xor_sync(MUX_FULL, fmin_, off, MUX_G));
+            fmax_ = fmaxf(fmax_, __shfl_xor_sync(MUX_FULL, fmax_, off, MUX_G));
+        }
+        const bool clearlyFine = fmin_ >= 0.011f * fmax_ && fmin_ > 0x1p-100f && fmax_ < 0x1p100f;
+        if (__any_sync(MUX_FULL, part && !clearlyFine)) {
+            const T smin = gmin8(fi ? d : Num<T>::inf());
+            const T amax = gmax8(fi ? d : -Num<T>::inf());
+            if (part && smin > (T)0) {
+                bool wellScaled;                       // the roots only near the boundary
+                if (smin >= (T)0.0102 * amax) wellScaled = true;
+                else if (smin <= (T)0.0098 * amax) wellScaled = false;
+                else wellScaled = div_ni(sqrt_ni(smin), sqrt_ni(amax)) >= (T)0.1;
+                equil = !(wellScaled && amax >= Num<T>::small_() && amax <= Num<T>::large_());
+            }
+        }
     }
     T s = (T)1;
-    if (equil) {
-        s = fi ? rcp_ni(sqrt_ni(d)) : (T)1;
+    if (__any_sync(MUX_FULL, equil)) {         // rare; groups that do not equilibrate scale by exactly 1
+        if (equil && fi) s = rcp_ni(sqrt_ni(d));
 #pragma unroll
-        for (int j = 0; j < G; ++j) { const T sj = gshfl(gmask, s, j); a[j] = (sj * s) * a[j]; }   // dlaqsy: cj * s(i) * A(i,j)
+        for (int j = 0; j < G; ++j) { const T sj = gshfl(s, j); a[j] = (sj * s) * a[j]; }          // dlaqsy: cj * s(i) * A(i,j)
         b = s * b;                                                                                 // dposvx: B := diag(S) B
     }
 #pragma unroll
@@ -130,19 +185,20 @@ __device__ __forceinline__ int posvx_dist(unsigned gmask, int gl, const T (&Prow
     // ?potrf, lower, right-looking: a[] becomes row gl of L (columns <= gl), ft[k] = L(k, gl) (row gl of L^T)
     T ft[G];
     T rinv = (T)0;
+    int info = 0;
 #pragma unroll
     for (int j = 0; j < G; ++j) ft[j] = (T)0;
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        const T ajj = gshfl(gmask, a[j], j);
-        if (ajj <= (T)0) return j + 1;         // breakdown (a NaN pivot passes through, as in OpenBLAS' potf2: `ajj <= 0`)
-        const T ljj = sqrt_ni(ajj);
-        const T r = rcp_ni(ljj);
+        const T ajj = gshfl(a[j], j);
+        if (info == 0 && ajj <= (T)0) info = j + 1;     // breakdown (a NaN pivot passes through, as in OpenBLAS' potf2: `ajj <= 0`)
+        T ljj, r;
+        mux_sqrt_rcp(ajj, ljj, r);
         const T fij = a[j] * r;                // L(gl, j) for gl > j
         if (gl == j) { a[j] = ljj; rinv = r; } else a[j] = fij;
 #pragma unroll
         for (int k = j + 1; k < G; ++k) {
-            const T fk = gshfl(gmask, fij, k); // L(k, j)
+            const T fk = gshfl(fij, k);        // L(k, j)
             a[k] = fma(-fij, fk, a[k]);        // a(gl, k) -= L(gl, j) L(k, j): the part k <= gl is the matrix, the rest is never read
             if (gl == j) ft[k] = fk;
         }
@@ -153,13 +209,13 @@ __device__ __forceinline__ int posvx_dist(unsigned gmask, int gl, const T (&Prow
 #pragma unroll
         for (int k = 0; k < G; ++k) {
             const T cand = acc * rinv;
-            const T vk = gshfl(gmask, cand, k);
+            const T vk = gshfl(cand, k);
             if (gl == k) acc = cand; else if (gl > k) acc = fma(-a[k], vk, acc);
         }
 #pragma unroll
         for (int k = G - 1; k >= 0; --k) {
             const T cand = acc * rinv;
-            const T xk = gshfl(gmask, cand, k);
+            const T xk = gshfl(cand, k);
             if (gl == k) acc = cand; else if (gl < k) acc = fma(-ft[k], xk, acc);
         }
         return acc;
@@ -171,14 +227,15 @@ __device__ __forceinline__ int posvx_dist(unsigned gmask, int gl, const T (&Prow
     const T safe1 = (T)(nfree + 1) * Num<T>::safmin();
     const T safe2 = safe1 * ((T)1 / Num<T>::lapack_eps());
     T lstres = (T)3, x = (T)0, v = b;
+    bool live = part && info == 0;
 #pragma unroll 1
     for (int count = 0;; ++count) {
-        v = solve(v);
-        x += v;
+        const T z = solve(v);
+        if (live) x += z;
         T r = b, w = t_abs(b);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-            const T xj = gshfl(gmask, x, j);
+            const T xj = gshfl(x, j);
             r = fma(-a0[j], xj, r);
             w = fma(t_abs(a0[j]), t_abs(xj), w);
         }
@@ -187,20 +244,22 @@ __device__ __forceinline__ int posvx_dist(unsigned gmask, int gl, const T (&Prow
             const bool big = w > safe2;
             qv = div_ni(big ? t_abs(r) : t_abs(r) + safe1, big ? w : w + safe1);
         }
-        const T berr = gmax8(gmask, qv);
+        const T berr = gmax8(qv);
         v = r;
-        if (!(berr > eps && (T)2 * berr <= lstres && count < 5)) break;      // at most ITMAX = 5 corrections
+        live = live && (berr > eps && (T)2 * berr <= lstres && count < 5);      // at most ITMAX = 5 corrections
         lstres = berr;
+        if (!__any_sync(MUX_FULL, live)) break;
     }
     x_out = equil ? x * s : x;
-    return 0;
+    return info;
 }
 
 // solveBoxQP, boxcqp.d:122-379 (unconstrainedSolution = false) with P = J^T J + lambda I, lane gl owning variable gl.
 // JJrow: row gl of the undamped J^T J.  q, l, u, x: this lane's entries (lanes >= n: q = 0, l = -inf, u = +inf).
+// Executed by all 32 lanes in lock step; groups with act == false run along and return mir_qp_solved.
 // Returns mir_box_qp_status, uniform over the group.
 template <class T, int N>
-__device__ __forceinline__ int boxqp_dist(unsigned gmask, int gl, int gshift, const typename Num<T>::QPSettings& st,
+__device__ __forceinline__ int boxqp_dist(bool act, int gl, int gshift, const typename Num<T>::QPSettings& st,
                                           const T (&JJrow)[MUX_G], T lambda, T q, T l, T u, T& x, QPCounters& cnt)
 {
     constexpr int G = MUX_G;
@@ -218,78 +277,97 @@ __device__ __forceinline__ int boxqp_dist(unsigned gmask, int gl, int gshift, co
     unsigned free = FULL, lo = 0, up = 0;
     bool first = true;
     unsigned step = 0;
+    int res = act ? -1 : (int)mir_qp_solved;                                             // -1: still running
     x = (T)0;
 #pragma unroll 1
     for (;;) {
-        if (free) {
+        const bool doSolve = res < 0 && free != 0u;
+        {
             T sx;
-            ++cnt.solves;
-            if (posvx_dist<T>(gmask, gl, Prow, Pdiag, free, b, sx) != 0) return mir_qp_numericError;   // BQ:212, 323
-            if ((free >> gl) & 1u) x = sx;                                               // BQ:327-329
+            const int info = posvx_dist<T>(doSolve, gl, Prow, Pdiag, free, b, sx);
+            if (doSolve) {
+                ++cnt.solves;
+                if (info != 0) res = mir_qp_numericError;                                // BQ:212, 323
+                else if ((free >> gl) & 1u) x = sx;                                      // BQ:327-329
+            }
         }
-        if (first) {
+        const bool wasFirst = first;
+        const bool inAll = gall8(!valid || (l <= x && x <= u), gshift);
+        if (res < 0 && first) {
             first = false;                                                               // BQ:216-219
-            if (__all_sync(gmask, !valid || (l <= x && x <= u))) return mir_qp_solved;
-        } else {
+            if (inAll) res = mir_qp_solved;
+        }
+        if (!__any_sync(MUX_FULL, res < 0)) break;
+        if (__any_sync(MUX_FULL, res < 0 && !wasFirst)) {
             T d1 = (T)0, d2 = (T)0;                                                      // multipliers, BQ:333-337
 #pragma unroll
             for (int j = 0; j < G; ++j) {
-                const T xj = gshfl(gmask, x, j);
+                const T xj = gshfl(x, j);
                 if (j < gl) d1 = fma(Prow[j], xj, d1); else d2 = fma(Prow[j], xj, d2);
             }
             const T val = d1 + d2 + q;
-            bool bad;
-            if ((lo >> gl) & 1u)      { la = val;  bad = !(val >= (T)0); }               // BQ:343
-            else if ((up >> gl) & 1u) { mu = -val; bad = !(-val >= (T)0); }              // BQ:344
-            else bad = valid && !(x >= l && x <= u);                                     // BQ:345
-            if (!__any_sync(gmask, bad)) {
-                x = t_max(t_min(x, u), l);                                               // applyBounds, BQ:349
-                return mir_qp_solved;
+            const bool mine = res < 0 && !wasFirst;
+            bool bad = false;
+            if (mine) {
+                if ((lo >> gl) & 1u)      { la = val;  bad = !(val >= (T)0); }           // BQ:343
+                else if ((up >> gl) & 1u) { mu = -val; bad = !(-val >= (T)0); }          // BQ:344
+                else bad = valid && !(x >= l && x <= u);                                 // BQ:345
             }
-            ++step;
+            const bool anyBad = gany8(bad, gshift);
+            if (mine) {
+                if (!anyBad) { x = t_max(t_min(x, u), l); res = mir_qp_solved; }         // applyBounds, BQ:349
+                else ++step;
+            }
+            if (!__any_sync(MUX_FULL, res < 0)) break;
         }
-        if (step >= maxIterations) return mir_qp_maxIterations;                          // BQ:378
-        ++cnt.iterations;
-
-        int mine = 0;                                                                    // BQ:239-263
-        if (valid) {
+        if (res < 0 && step >= maxIterations) res = mir_qp_maxIterations;                // BQ:378
+        const bool run = res < 0;
+        if (run) ++cnt.iterations;
+        int cls = 0;                                                                     // BQ:239-263
+        if (run && valid) {
             const T xl = x - l, ux = u - x;
-            if (xl < (T)0 || (xl < st.relTolerance + st.absTolerance * t_abs(l) && la >= (T)0)) { mine = 1; x = l; mu = (T)0; }
-            else if (ux < (T)0 || (ux < st.relTolerance + st.absTolerance * t_abs(u) && mu >= (T)0)) { mine = 2; x = u; la = (T)0; }
+            if (xl < (T)0 || (xl < st.relTolerance + st.absTolerance * t_abs(l) && la >= (T)0)) { cls = 1; x = l; mu = (T)0; }
+            else if (ux < (T)0 || (ux < st.relTolerance + st.absTolerance * t_abs(u) && mu >= (T)0)) { cls = 2; x = u; la = (T)0; }
             else { mu = (T)0; la = (T)0; }
         }
-        lo = (__ballot_sync(gmask, mine == 1) >> gshift) & FULL;
-        up = (__ballot_sync(gmask, mine == 2) >> gshift) & FULL;
+        const unsigned lon = (__ballot_sync(MUX_FULL, cls == 1) >> gshift) & FULL;
+        const unsigned upn = (__ballot_sync(MUX_FULL, cls == 2) >> gshift) & FULL;
+        if (run) {
+            lo = lon; up = upn;
+            free = FULL & ~(lo | up);
+            if (free == FULL) res = mir_qp_maxIterations;                                // BQ:265-266: `break` falls out to :378
+        }
         const unsigned fixed = lo | up;
-        free = FULL & ~fixed;
-        if (free == FULL) return mir_qp_maxIterations;                                   // BQ:265-266: `break` falls out to :378
-
-        const T bound = (mine == 1) ? l : u;                                             // reduced right-hand side, BQ:282-305
+        const T bound = (cls == 1) ? l : u;                                              // reduced right-hand side, BQ:282-305
         KBN<T> sum(q);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-            const T bj = gshfl(gmask, bound, j);
+            const T bj = gshfl(bound, j);
             if ((fixed >> j) & 1u) sum.put(mul_rn(Prow[j], bj));
         }
-        b = -sum.sum();
+        if (res < 0) b = -sum.sum();
+        if (!__any_sync(MUX_FULL, res < 0)) break;
     }
+    return res;
 }
 
-template <class Model, class T, bool FD>
-__global__ void __launch_bounds__(MUX_WARPS * 32, 1)
+template <class Model, class T, bool ON> struct SharedFD { struct State {}; static constexpr int CPI = 1; };
+template <class Model, class T> struct SharedFD<Model, T, true> { using State = typename Model::template FDState<MUX_R>; static constexpr int CPI = Model::CPI; };
+
+template <class Model, class T, bool FD, int MUX_WARPS>
+__global__ void __launch_bounds__(32 * MUX_WARPS)
 lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
 {
-    constexpr int N = Model::N, G = MUX_G, S = MUX_SLOTS, R = MUX_R;
-    constexpr int NP = N * (N + 1) / 2, K = NP + N;
-    constexpr int NE = Model::NE;
+    constexpr int N = Model::N, G = MUX_G, S = MUX_SLOTS, R = MUX_R, NE = Model::NE;
     static_assert(N <= G, "lm_mux_kernel: at most 8 parameters");
+    static_assert(NE >= 1 && NE <= 4, "lm_mux_kernel: models with 1..4 exponentials per row");
+    constexpr int KB = NE * R;                // exponentials per evaluation of my four rows (<= 16), interleaved in one exp block
+    constexpr bool kShared = FD && Model::kFDShared;
     using Result = typename Num<T>::Result;
-    constexpr unsigned FULLW = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char mux_smem_raw[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    MuxWarpSmem<T>& sm = reinterpret_cast<MuxWarpSmem<T>*>(mux_smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
     const int grp = lane >> 3, gl = lane & 7, gshift = grp * 8;
-    const unsigned gmask = 0xffu << gshift;
-    MuxWarpSmem<T>& sm = reinterpret_cast<MuxWarpSmem<T>*>(mux_smem_raw)[wid];
     const bool valid = gl < N;
     const int m = (int)args.m;
     const bool gridPerProblem = (args.flags & MIR_MODEL_GRID_PER_PROBLEM) != 0;
@@ -297,241 +375,392 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
     const T* __restrict__ tptr = static_cast<const T*>(args.t);
     const T* __restrict__ yptr = static_cast<const T*>(args.y);
 
-    for (int e = lane; e < S * G * G; e += 32) (&sm.JJ[0][0])[e] = (T)0;     // rows / columns >= n stay zero for good
-    for (int e = lane; e < S * G; e += 32) (&sm.Jy[0][0])[e] = (T)0;
+    for (int e = lane; e < (int)(sizeof(MuxWarpSmem<T>) / sizeof(T)); e += 32) reinterpret_cast<T*>(&sm)[e] = (T)0;
     __syncwarp();
 
-    // ---- warp-role state: my rows (lane + 32 k) of the four problems of this warp
+    // ---- warp-role state: the shared abscissa of my rows (lane + 32 k)
     T tts[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) { const int row = lane + 32 * k; tts[k] = (Model::kHasData && !gridPerProblem && row < m) ? tptr[row] : (T)0; }
-    T yv[S][R], mb[S][R], yo[S][R];           // y (current residuals), mBuffer (trial residuals), observations
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int k = 0; k < R; ++k) { yv[s][k] = (T)0; mb[s][k] = (T)0; yo[s][k] = (T)0; }
 
     // ---- group-role state: problem `grp` of this warp, parameter gl.  Scalars are bit-identical in the 8 lanes.
-    bool active = false, retired = false, init = false;
+    bool active = false, retired = false, init = false, finished = false, passOpen = false, skipRest = false;
     unsigned long long prob = 0;
+    int ysel = 0, jacMode = 0;
     T x = (T)0, xt = (T)0, dX = (T)0, Jy = (T)0, lo = -Num<T>::inf(), up = Num<T>::inf();
     T lambda = (T)0, mu = (T)1, residual = Num<T>::inf(), deltaX_dot = (T)0, nd = (T)0, trial = (T)0;
+    T fd_xp = (T)0, fd_xm = (T)0, fd_rt = (T)0;
     unsigned age = 0, maxAge = 1, iterations = 0, fCalls = 0, gCalls = 0;
     int status = mir_ls_numericError;
     bool needJacobian = false, fConverged = false;
     unsigned sPasses = 0, sAccepted = 0, sFresh = 0, sBroyden = 0, sEvals = 0, sSolves = 0, sQPIt = 0, sProblems = 0;
 
-    // Residuals of MY rows of one problem at parameter vector p: out[k] = r_row(p), returns the lane's partial ||r||^2.
-    // The exps of two rows (2 NE independent chains) go through one interleaved exp_repro_many call.
-    auto eval_rows = [&](const T (&p)[N], const T (&tk)[R], const T (&yk)[R], T (&out)[R]) -> T {
-        const typename Model::Pre pre = Model::prepare(p);
-        T part = (T)0;
-#pragma unroll
-        for (int k = 0; k < R; k += 2) {
-            T r0, r1;
-            if constexpr (NE > 0) {
-                T ea[2 * NE], ee[2 * NE];
-                Model::exp_args(pre, p, tk[k], ea); Model::exp_args(pre, p, tk[k + 1], ea + NE);
-                exp_repro_many<2 * NE>(ea, ee);
-                Model::finish_r(pre, p, tk[k], yk[k], ee, r0); Model::finish_r(pre, p, tk[k + 1], yk[k + 1], ee + NE, r1);
-            } else {
-                r0 = Model::residual(pre, p, lane + 32 * k, tk[k], yk[k]); r1 = Model::residual(pre, p, lane + 32 * (k + 1), tk[k + 1], yk[k + 1]);
-            }
-            r0 = (lane + 32 * k < m) ? r0 : (T)0; r1 = (lane + 32 * (k + 1) < m) ? r1 : (T)0;
-            out[k] = r0; out[k + 1] = r1;
-            part += r0 * r0; part += r1 * r1;
-        }
-        return part;
-    };
-
     for (;;) {
-        // =============================================================== phase 0 (groups): refill, guards LS:974-995, Jacobian decision LS:996-1015
-        int jacMode = MUX_JAC_NONE;
-        bool doEval = false, evalInit = false, finished = false, skipRest = false, accepted = false;
-        T fd_xp = (T)0, fd_xm = (T)0, fd_rt = (T)0;
-        if (!active && !retired) {
-            unsigned int idx = 0, staged = 1;
-            if (gl == 0) {
-                idx = atomicAdd(args.counter, 1u);
-                if (idx < args.batch) staged = wait_staged(args.ready, idx, args.spin_limit) ? 1u : 0u;
-            }
-            idx = gshfl(gmask, idx, 0); staged = gshfl(gmask, staged, 0);
-            if (idx >= args.batch) retired = true;
-            else {
-                ++sProblems;
-                if (!staged) {                     // inputs never arrived: the host discards this launch (flag ready[1]); do not touch x
-                    if (gl == 0) {
-                        Result bad;
-                        bad.status = mir_ls_numericError; bad.iterations = 0; bad.fCalls = 0; bad.gCalls = 0; bad.residual = Num<T>::inf(); bad.lambda = (T)0;
-                        static_cast<Result*>(args.results)[idx] = bad;
-                    }
-                } else {
-                    prob = idx;
-                    x = valid ? static_cast<const T*>(args.x)[prob * N + gl] : (T)0;
-                    lo = valid ? static_cast<const T*>(args.l)[prob * args.bound_stride + gl] : -Num<T>::inf();
-                    up = valid ? static_cast<const T*>(args.u)[prob * args.bound_stride + gl] : Num<T>::inf();
-                    // validation, LS:930-943 (first failure wins)
-                    const bool finite = __all_sync(gmask, !valid || (-Num<T>::inf() < x && x < Num<T>::inf()));
-                    const bool inb = __all_sync(gmask, !valid || ((lo <= x) && (x <= up)));
-                    int vs = 0;
-                    if (m == 0 || !finite) vs = mir_ls_badGuess;
-                    else if (!inb) vs = mir_ls_badBounds;
-                    else if (!((T)0 <= st.minStepQuality && st.minStepQuality < (T)1)) vs = mir_ls_badMinStepQuality;
-                    else if (!((T)0 <= st.goodStepQuality && st.goodStepQuality <= (T)1)) vs = mir_ls_badGoodStepQuality;
-                    else if (!(st.minStepQuality < st.goodStepQuality)) vs = mir_ls_badStepQuality;
-                    else if (!((T)1 <= st.lambdaIncrease && st.lambdaIncrease <= Num<T>::sqrt_max())) vs = mir_ls_badLambdaParams;
-                    else if (!(Num<T>::sqrt_min_normal() <= st.lambdaDecrease && st.lambdaDecrease <= (T)1)) vs = mir_ls_badLambdaParams;
-                    if (vs) {
-                        if (gl == 0) {
-                            Result ret;
-                            ret.status = vs; ret.iterations = 0; ret.fCalls = 0; ret.gCalls = 0; ret.residual = Num<T>::inf(); ret.lambda = (T)0;
-                            static_cast<Result*>(args.results)[prob] = ret;                  // x is left untouched
-                        }
-                    } else {
-                        active = true; init = true;
-                        xt = x; dX = (T)0; Jy = (T)0;
-                        maxAge = st.maxAge ? st.maxAge : (FD ? 2u * N : 3u);                                 // LS:945
-                        iterations = 0; fCalls = 0; gCalls = 0; status = mir_ls_maxIterations;               // LS:959-971
-                        residual = Num<T>::inf(); lambda = (T)0; mu = (T)1; deltaX_dot = (T)0;
-                        age = maxAge; needJacobian = false; fConverged = false;
-                    }
-                }
-            }
-        }
-        if (active) {
-            if (init) { doEval = true; evalInit = true; }                                                    // initial residual, LS:953-956
-            else {
-                ++sPasses;
-                if (fConverged) { status = mir_ls_fConverged; finished = true; }                             // LS:974-978
-                else if (!(lambda <= st.maxLambda)) { status = mir_ls_furtherImprovement; finished = true; } // LS:979-983
-                else {
-                    if (mu > (T)16 && age) { needJacobian = true; age = maxAge; mu = (T)1; }                 // LS:984-989
-                    if (__any_sync(gmask, valid && !(x <= x))) { status = mir_ls_numericError; finished = true; }   // LS:990-995
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            int rf = 0;                        // row work this group's slot asks for (MUX_EVAL_* / MUX_JAC_*)
+            if (half == 0) {
+                // ======================================================= close the open pass: accept / reject, LS:1117-1175
+                const bool closing = active && !finished && passOpen;
+                bool accepted = false;
+                T improvement = (T)0;
+                if (closing && !skipRest) {
+                    if (!(trial <= Num<T>::inf())) { status = mir_ls_numericError; finished = true; }        // LS:1117-1122
                     else {
-                        bool inert = false;
-                        if (!needJacobian && age == 0 && tailShortcut) {
-                            // tail_is_inert (lm_small.cuh), distributed: lane gl holds x_gl, (J^T y)_gl and row gl of J^T J
-                            const T q2 = gsum8(gmask, Jy * Jy);
-                            const T xmin = gmin8(gmask, valid ? t_abs(x) : Num<T>::inf());
-                            if (xmin > (T)0 && st.maxStep > (T)0 && sqrt_ni(q2) < lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125))) {
-                                const bool strict = __all_sync(gmask, !valid || ((lo < x) && (x < up)));
-                                const bool inside = __all_sync(gmask, !valid || ((lo <= x) && (x <= up)));
-                                if (strict) inert = true;
-                                else if (inside) {                                                           // tail_bounds_certificate
-                                    T row = (T)0;
+                        improvement = residual - trial;                                                      // LS:1124
+                        if (!(improvement > (T)0)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; }         // LS:1125-1130
+                        else accepted = true;
+                    }
+                }
+                if (__any_sync(MUX_FULL, accepted)) {
+                    T acc = (T)0;                                                                            // symv(Lower, 1, JJ, deltaX, 2, Jy), LS:1141
 #pragma unroll
-                                    for (int j = 0; j < G; ++j) row += t_abs(sm.JJ[grp][gl * G + j]);
-                                    const T nu = gmax8(gmask, row), qinf = gmax8(gmask, t_abs(Jy));
-                                    const T thr = ((T)8 * nu) * (qinf / lambda), dmax = xmin * (Num<T>::lapack_eps() * (T)0.25);
-                                    const T ql = lo - x, qu = up - x;
-                                    const bool onL = ql == (T)0, onU = qu == (T)0;
-                                    const bool farL = (-ql - dmax) >= (T)2 * (st.qpSettings.relTolerance + st.qpSettings.absTolerance * t_abs(ql));
-                                    const bool farU = (qu - dmax) >= (T)2 * (st.qpSettings.relTolerance + st.qpSettings.absTolerance * t_abs(qu));
-                                    bool ok;
-                                    if (onL && onU) ok = false;
-                                    else if (onL || onU) ok = (onL ? farU : farL) && (t_abs(Jy) >= thr);
-                                    else ok = farL && farU;
-                                    inert = (lambda >= (T)4 * nu) && __all_sync(gmask, !valid || ok);
-                                }
+                    for (int j = 0; j < G; ++j) acc = fma(sm.JJ[grp][gl * G + j], gshfl(dX, j), acc);
+                    const T Jy2 = acc + (T)2 * Jy;
+                    const T pred = -gsum8(Jy2 * dX);                                                         // LS:1142
+                    T xss = gsum8(valid ? xt * xt : (T)0);                                                   // LS:1164: nrm2(x)
+                    T xsc = (T)1;
+                    if (__any_sync(MUX_FULL, accepted && !(xss >= Num<T>::small_() && xss <= Num<T>::large_()))) {   // BLAS scales: so do we when it matters
+                        const T xmax = gmax8(valid ? t_abs(xt) : (T)0);
+                        xsc = (xmax > (T)0 && xmax < Num<T>::inf()) ? xmax : (T)1;
+                        const T vx = valid ? xt * rcp_ni(xsc) : (T)0;
+                        xss = gsum8(vx * vx);
+                    }
+                    const T xn = xsc * sqrt_ni(xss);
+                    if (accepted) {
+                        needJacobian = true; mu = (T)1; ++iterations; ++sAccepted;                           // LS:1132-1139
+                        x = xt; ysel ^= 1;                     // the reference swaps the slices y / mBuffer, LS:1136
+                        residual = trial;
+                        fConverged = residual <= st.maxGoodResidual;
+                        deltaX_dot = nd;
+                        Jy = Jy2;                              // (scratch from here, as in the reference)
+                        if (!(pred > (T)0)) { status = mir_ls_furtherImprovement; finished = true; }         // LS:1144-1148
+                        else {
+                            const T rho = div_ni(pred, improvement);                                         // LS:1150
+                            if (rho < st.minStepQuality) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; }   // LS:1152-1156
+                            else if (rho >= st.goodStepQuality) lambda = t_max(st.lambdaDecrease * lambda * mu, st.minLambda);   // LS:1158-1161
+                            const T sd = sqrt_ni(deltaX_dot);
+                            if (!(sd > st.absTolerance && xn > sd * st.relTolerance)) {                      // LS:1164-1173
+                                if (age == 0) { status = mir_ls_xConverged; finished = true; }
+                                else age = maxAge;
                             }
                         }
-                        if (inert) {
-                            for (;;) {                         // replay LS:1112, 1125-1130 and the next pass's LS:979-983
-                                ++fCalls;
-                                lambda *= st.lambdaIncrease * mu; mu *= (T)2;
-                                ++sPasses;
-                                if (!(lambda <= st.maxLambda)) break;
+                    }
+                }
+                if (closing && !finished && !(iterations < st.maxIterations)) { status = mir_ls_maxIterations; finished = true; }   // LS:1175
+                passOpen = false;
+
+                // ======================================================= next pass: guards LS:974-995, Jacobian decision LS:996-1015
+                bool open = false;
+                if (active && !finished && !init) {
+                    ++sPasses;
+                    if (fConverged) { status = mir_ls_fConverged; finished = true; }                             // LS:974-978
+                    else if (!(lambda <= st.maxLambda)) { status = mir_ls_furtherImprovement; finished = true; } // LS:979-983
+                    else {
+                        if (mu > (T)16 && age) { needJacobian = true; age = maxAge; mu = (T)1; }                 // LS:984-989
+                        open = true;
+                    }
+                }
+                if (gany8(valid && !(x <= x), gshift) && open) { status = mir_ls_numericError; finished = true; open = false; }   // LS:990-995
+                const bool wantTail = open && !needJacobian && age == 0 && tailShortcut;
+                if (__any_sync(MUX_FULL, wantTail)) {
+                    // tail_is_inert (lm_small.cuh), distributed: lane gl holds x_gl, (J^T y)_gl and row gl of J^T J
+                    const T q2 = gsum8(Jy * Jy);
+                    const T xmin = gmin8(valid ? t_abs(x) : Num<T>::inf());
+                    const bool small = xmin > (T)0 && st.maxStep > (T)0 && sqrt_ni(q2) < lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125));
+                    const bool strict = gall8(!valid || ((lo < x) && (x < up)), gshift);
+                    const bool inside = gall8(!valid || ((lo <= x) && (x <= up)), gshift);
+                    bool inert = wantTail && small && strict;
+                    if (__any_sync(MUX_FULL, wantTail && small && !strict && inside)) {                          // tail_bounds_certificate
+                        T row = (T)0;
+#pragma unroll
+                        for (int j = 0; j < G; ++j) row += t_abs(sm.JJ[grp][gl * G + j]);
+                        const T nu = gmax8(row), qinf = gmax8(t_abs(Jy));
+                        const T thr = ((T)8 * nu) * (qinf / lambda), dmax = xmin * (Num<T>::lapack_eps() * (T)0.25);
+                        const T ql = lo - x, qu = up - x;
+                        const bool onL = ql == (T)0, onU = qu == (T)0;
+                        const bool farL = (-ql - dmax) >= (T)2 * (st.qpSettings.relTolerance + st.qpSettings.absTolerance * t_abs(ql));
+                        const bool farU = (qu - dmax) >= (T)2 * (st.qpSettings.relTolerance + st.qpSettings.absTolerance * t_abs(qu));
+                        bool ok;
+                        if (onL && onU) ok = false;
+                        else if (onL || onU) ok = (onL ? farU : farL) && (t_abs(Jy) >= thr);
+                        else ok = farL && farU;
+                        const bool allOk = gall8(!valid || ok, gshift);
+                        if (wantTail && small && !strict && inside) inert = (lambda >= (T)4 * nu) && allOk;
+                    }
+                    if (inert) {
+                        for (;;) {                             // replay LS:1112, 1125-1130 and the next pass's LS:979-983
+                            ++fCalls;
+                            lambda *= st.lambdaIncrease * mu; mu *= (T)2;
+                            ++sPasses;
+                            if (!(lambda <= st.maxLambda)) break;
+                        }
+                        status = mir_ls_furtherImprovement; finished = true; open = false;
+                    }
+                }
+                jacMode = 0;
+                if (open) {
+                    passOpen = true; skipRest = false;
+                    if (needJacobian) {                                                                          // LS:996-998
+                        needJacobian = false;
+                        if (age < maxAge) { ++age; jacMode = MUX_JAC_BROYDEN; ++sBroyden; }                      // LS:999-1007
+                        else {
+                            age = 0; jacMode = MUX_JAC_FRESH; ++sFresh;                                          // LS:1010
+                            if (FD) fCalls += N; else gCalls += 1;                                               // LS:1049 (counts tasks) / LS:1014
+                            if constexpr (FD) {                                                                  // LS:1026-1033, parameter gl
+                                fd_xm = t_max(x - st.jacobianEpsilon, lo);
+                                fd_xp = t_min(x + st.jacobianEpsilon, up);
+                                const T twh = fd_xp - fd_xm;
+                                fd_rt = (twh != (T)0) ? rcp_ni(twh) : (T)0;      // 0 marks "column = 0" (LS:1045-1047); 1 / twh is never 0
                             }
-                            status = mir_ls_furtherImprovement; finished = true;
-                        } else if (needJacobian) {                                                           // LS:996-998
-                            needJacobian = false;
-                            if (age < maxAge) { ++age; jacMode = MUX_JAC_BROYDEN; ++sBroyden; }              // LS:999-1007
-                            else {
-                                age = 0; jacMode = MUX_JAC_FRESH; ++sFresh;                                  // LS:1010
-                                if (FD) fCalls += N; else gCalls += 1;                                       // LS:1049 (counts tasks) / LS:1014
-                                if constexpr (FD) {                                                          // LS:1026-1033, parameter gl
-                                    fd_xm = t_max(x - st.jacobianEpsilon, lo);
-                                    fd_xp = t_min(x + st.jacobianEpsilon, up);
-                                    const T twh = fd_xp - fd_xm;
-                                    fd_rt = (twh != (T)0) ? rcp_ni(twh) : (T)0;      // 0 marks "column = 0" (LS:1045-1047); 1 / twh is never 0
+                        }
+                    }
+                    rf = jacMode;
+                }
+
+                // ======================================================= retire finished problems, refill the slot
+                if (active && finished) {
+                    if (valid) static_cast<T*>(args.x)[prob * N + gl] = x;
+                    if (gl == 0) {
+                        Result ret;
+                        ret.status = status; ret.iterations = iterations; ret.fCalls = fCalls; ret.gCalls = gCalls;
+                        ret.residual = residual; ret.lambda = lambda;
+                        static_cast<Result*>(args.results)[prob] = ret;
+                    }
+                    active = false;
+                }
+                if (__any_sync(MUX_FULL, !active && !retired)) {
+                    const bool want = !active && !retired;
+                    unsigned int idx = 0, staged = 1;
+                    if (want && gl == 0) {
+                        idx = atomicAdd(args.counter, 1u);
+                        if (idx < args.batch) staged = wait_staged(args.ready, idx, args.spin_limit) ? 1u : 0u;
+                    }
+                    idx = gshfl(idx, 0); staged = gshfl(staged, 0);
+                    const bool take = want && idx < args.batch && staged;
+                    T nx = (T)0, nlo = -Num<T>::inf(), nup = Num<T>::inf();
+                    if (take && valid) {
+                        nx = static_cast<const T*>(args.x)[(unsigned long long)idx * N + gl];
+                        nlo = static_cast<const T*>(args.l)[(unsigned long long)idx * args.bound_stride + gl];
+                        nup = static_cast<const T*>(args.u)[(unsigned long long)idx * args.bound_stride + gl];
+                    }
+                    // validation, LS:930-943 (first failure wins)
+                    const bool finite = gall8(!valid || (-Num<T>::inf() < nx && nx < Num<T>::inf()), gshift);
+                    const bool inb = gall8(!valid || ((nlo <= nx) && (nx <= nup)), gshift);
+                    if (want) {
+                        if (idx >= args.batch) retired = true;
+                        else {
+                            ++sProblems;
+                            int vs = 0;
+                            if (!staged) vs = mir_ls_numericError;     // inputs never arrived: the host discards this launch (flag ready[1])
+                            else if (m == 0 || !finite) vs = mir_ls_badGuess;
+                            else if (!inb) vs = mir_ls_badBounds;
+                            else if (!((T)0 <= st.minStepQuality && st.minStepQuality < (T)1)) vs = mir_ls_badMinStepQuality;
+                            else if (!((T)0 <= st.goodStepQuality && st.goodStepQuality <= (T)1)) vs = mir_ls_badGoodStepQuality;
+                            else if (!(st.minStepQuality < st.goodStepQuality)) vs = mir_ls_badStepQuality;
+                            else if (!((T)1 <= st.lambdaIncrease && st.lambdaIncrease <= Num<T>::sqrt_max())) vs = mir_ls_badLambdaParams;
+                            else if (!(Num<T>::sqrt_min_normal() <= st.lambdaDecrease && st.lambdaDecrease <= (T)1)) vs = mir_ls_badLambdaParams;
+                            if (vs) {
+                                if (gl == 0) {                     // x is left untouched
+                                    Result ret;
+                                    ret.status = vs; ret.iterations = 0; ret.fCalls = 0; ret.gCalls = 0; ret.residual = Num<T>::inf(); ret.lambda = (T)0;
+                                    static_cast<Result*>(args.results)[idx] = ret;
                                 }
+                            } else {
+                                active = true; init = true; finished = false; passOpen = false; skipRest = false;
+                                prob = idx; x = nx; lo = nlo; up = nup;
+                                xt = x; dX = (T)0; Jy = (T)0; ysel = 0;
+                                maxAge = st.maxAge ? st.maxAge : (FD ? 2u * N : 3u);                                 // LS:945
+                                iterations = 0; fCalls = 0; gCalls = 0; status = mir_ls_maxIterations;               // LS:959-971
+                                residual = Num<T>::inf(); lambda = (T)0; mu = (T)1; deltaX_dot = (T)0;
+                                age = maxAge; needJacobian = false; fConverged = false; jacMode = 0;
+                                rf = MUX_EVAL_INIT;                                                                  // initial residual, LS:953-956
+                            }
+                        }
+                    }
+                }
+                if constexpr (MUX_WARPS == 1) { if (__all_sync(MUX_FULL, retired)) goto done; }
+                else { if (__syncthreads_and(retired)) goto done; }
+            } else {
+                // ======================================================= the initial residual has arrived, LS:953-971
+                bool go = active && !finished && passOpen;
+                if (active && init) {
+                    init = false; go = false;
+                    residual = trial; fCalls = 1;
+                    fConverged = residual <= st.maxGoodResidual;
+                    needJacobian = true; age = maxAge;
+                }
+                // ======================================================= g-test LS:1053-1062
+                const bool jacd = go && jacMode != 0;
+                if (__any_sync(MUX_FULL, jacd)) {
+                    const T jyn = valid ? sm.Jy[grp][gl] : (T)0;
+                    T gsel = gmax8(t_abs(jyn));                    // iamax picks the first max |.|: its magnitude is the max
+                    const T j0 = gshfl(jyn, 0);
+                    if (!(j0 == j0)) gsel = j0;                    // BLAS: a NaN wins iamax only as the first element
+                    if (jacd) {
+                        Jy = jyn;
+                        if (!(gsel > st.gradTolerance)) {
+                            go = false;
+                            if (age == 0) { status = mir_ls_gConverged; finished = true; }
+                            else { age = maxAge; skipRest = true; }
+                        }
+                    }
+                }
+                // ======================================================= lambda LS:1067-1072, BOXCQP LS:1074-1085, trial point LS:1087-1112
+                if (__any_sync(MUX_FULL, go)) {
+                    T JJrow[G];
+                    T JJdiag = (T)0;
+#pragma unroll
+                    for (int j = 0; j < G; ++j) { JJrow[j] = sm.JJ[grp][gl * G + j]; JJdiag = (j == gl) ? JJrow[j] : JJdiag; }
+                    const T dmax = gmax8(valid ? JJdiag : (T)0);          // diag[iamax]; the diagonal of J^T J is >= 0
+                    if (go && !(lambda >= st.minLambda)) {                                                       // LS:1067-1072
+                        lambda = (T)(0.001 * (double)dmax);
+                        if (!(lambda >= st.minLambda)) lambda = (T)1;
+                    }
+                    QPCounters qc{0, 0};
+                    T dXn;
+                    const int qps = boxqp_dist<T, N>(go, gl, gshift, st.qpSettings, JJrow, lambda, Jy, lo - x, up - x, dXn, qc);   // LS:1074-1080
+                    sSolves += qc.solves; sQPIt += qc.iterations;
+                    const bool nan = gany8(valid && !(dXn <= dXn), gshift);                                      // LS:1087-1092
+                    const T dXr = valid ? add_rn(add_rn(dXn, x), -x) : (T)0;                                     // LS:1096-1097
+                    const T ndn = gsum8(dXr * dXr);                                                              // LS:1099
+                    const T xtn = valid ? t_max(t_min(add_rn(dXr, x), up), lo) : (T)0;                           // LS:1108-1110
+                    const bool same = gall8(!valid || ((xtn == x) && (signbit(xtn) == signbit(x))), gshift);
+                    const T sdn = sqrt_ni(ndn);
+                    if (go) {
+                        if (qps != mir_qp_solved || nan) { status = mir_ls_numericError; finished = true; }      // LS:1080-1092
+                        else {
+                            dX = dXr; nd = ndn;
+                            if (!(sdn < st.maxStep)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; skipRest = true; }   // LS:1101-1106
+                            else {
+                                xt = xtn;
+                                ++fCalls;                                                                        // LS:1112
+                                if (same) trial = residual;       // f(xt) == y bit for bit: evaluation skipped, a rejection follows
+                                else rf = MUX_EVAL_TRIAL;
                             }
                         }
                     }
                 }
             }
-        }
-        __syncwarp();
-        if (__all_sync(FULLW, retired)) break;
 
-        // =============================================================== phase 1 (warp): Jacobian step of each slot that needs one, then J^T y, J^T J
-        {
-            const int flags = (active && !finished) ? jacMode : 0;
+            // =========================================================== row phase (warp): the slots' requests, one slot at a time
+            if constexpr (MUX_WARPS > 1) { if (half == 1) __syncthreads(); }
 #pragma unroll 1
             for (int s = 0; s < S; ++s) {
-                const int mode = __shfl_sync(FULLW, flags, s * G);
-                if (mode == MUX_JAC_NONE) continue;
+                const int f = __shfl_sync(MUX_FULL, rf, s * G);
+                if (f == 0) continue;
+                const unsigned long long sprob = __shfl_sync(MUX_FULL, prob, s * G);
+                const int ys = __shfl_sync(MUX_FULL, ysel, s * G);
+                T* const yv = sm.vec[s][ys];
+                T* const mv = sm.vec[s][ys ^ 1];
+                const bool evalOnly = (f & (MUX_EVAL_INIT | MUX_EVAL_TRIAL)) != 0;
                 T p[N];
+                {
+                    const T src = (f & MUX_EVAL_TRIAL) ? xt : x;
 #pragma unroll
-                for (int j = 0; j < N; ++j) p[j] = __shfl_sync(FULLW, x, s * G + j);
-                const unsigned long long sprob = __shfl_sync(FULLW, prob, s * G);
+                    for (int j = 0; j < N; ++j) p[j] = __shfl_sync(MUX_FULL, src, s * G + j);
+                }
                 T tk[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     const int row = lane + 32 * k;
                     tk[k] = gridPerProblem ? ((Model::kHasData && row < m) ? tptr[sprob * (unsigned long long)m + row] : (T)0) : tts[k];
                 }
-                if (mode == MUX_JAC_FRESH) {
-                    if constexpr (FD) {                                                                      // LS:1018-1049
-                        T yos[R];
+
+                if (evalOnly || (f & MUX_JAC_FRESH)) {
+                    T yo[R];
 #pragma unroll
-                        for (int k = 0; k < R; ++k) yos[k] = slot_get(yo, s, k);
+                    for (int k = 0; k < R; ++k) {
+                        const int row = lane + 32 * k;
+                        yo[k] = (Model::kHasData && row < m && (evalOnly || FD)) ? yptr[sprob * (unsigned long long)m + row] : (T)0;
+                    }
+                    T* const dst = (f & MUX_EVAL_INIT) ? yv : mv;
+                    T part = (T)0;
+                    // evaluation items.  evalOnly: one evaluation at p.  Fresh analytic Jacobian: one item that delivers
+                    // Jacobian rows.  Fresh finite-difference Jacobian: 2 N evaluations, (column j, +h) then (column j, -h),
+                    // LS:1018-1049 -- or, for models that share sub-expressions between those evaluations
+                    // (Model::kFDShared, models.cuh), 1 + NE / CPI items.
+                    const bool shared = kShared && !evalOnly;
+                    int nItems = (evalOnly || !FD) ? 1 : 2 * N;
+                    if constexpr (kShared) { if (shared) nItems = 1 + NE / Model::CPI; }
+                    [[maybe_unused]] typename SharedFD<Model, T, kShared>::State fds = {};
+                    if (lane == s * G && !evalOnly && FD) sEvals += 2u * N;
 #pragma unroll 1
-                        for (int j = 0; j < N; ++j) {
-                            const T xp_ = __shfl_sync(FULLW, fd_xp, s * G + j), xm_ = __shfl_sync(FULLW, fd_xm, s * G + j);
-                            const T rt_ = __shfl_sync(FULLW, fd_rt, s * G + j);
-                            T col[R];
+                    for (int it = 0; it < nItems; ++it) {
+                        const int j = it >> 1, sgn = it & 1;
+                        T pp[N], ea[KB], ee[KB];
+                        T rt = (T)0;
+                        constexpr int CPI = SharedFD<Model, T, kShared>::CPI;
+                        [[maybe_unused]] T xpr[CPI], xmr[CPI], rtr[CPI], xpa[CPI], xma[CPI], rta[CPI];
+                        if constexpr (kShared) {
+                            if (shared) {
 #pragma unroll
-                            for (int k = 0; k < R; ++k) col[k] = (T)0;
-                            if (rt_ != (T)0) {
-                                T fp[R];
-#pragma unroll
-                                for (int k = 0; k < R; ++k) fp[k] = (T)0;
-#pragma unroll 1
-                                for (int sgn = 0; sgn < 2; ++sgn) {
-                                    T pp[N], f[R];
-#pragma unroll
-                                    for (int i = 0; i < N; ++i) pp[i] = (i == j) ? (sgn ? xm_ : xp_) : p[i];
-                                    eval_rows(pp, tk, yos, f);
-#pragma unroll
-                                    for (int k = 0; k < R; ++k) {
-                                        if (sgn == 0) fp[k] = f[k];
-                                        else col[k] = (fp[k] - f[k]) * rt_;                                  // LS:1040-1042
-                                    }
+                                for (int c = 0; c < CPI; ++c) {
+                                    const int kc = (it >= 1) ? (it - 1) * CPI + c : 0;
+                                    xpr[c] = __shfl_sync(MUX_FULL, fd_xp, s * G + 2 * kc + 1); xmr[c] = __shfl_sync(MUX_FULL, fd_xm, s * G + 2 * kc + 1);
+                                    rtr[c] = __shfl_sync(MUX_FULL, fd_rt, s * G + 2 * kc + 1);
+                                    xpa[c] = __shfl_sync(MUX_FULL, fd_xp, s * G + 2 * kc); xma[c] = __shfl_sync(MUX_FULL, fd_xm, s * G + 2 * kc);
+                                    rta[c] = __shfl_sync(MUX_FULL, fd_rt, s * G + 2 * kc);
                                 }
-                                if (lane == s * G) sEvals += 2;
                             }
-#pragma unroll
-                            for (int k = 0; k < R; ++k) sm.J[s][j][lane + 32 * k] = col[k];
                         }
-                    } else {                                                                                 // LS:1011-1015
-                        const typename Model::Pre pre = Model::prepare(p);
+                        if (FD && !evalOnly && !kShared) {
+                            const T xpm = __shfl_sync(MUX_FULL, sgn ? fd_xm : fd_xp, s * G + j);
+                            rt = __shfl_sync(MUX_FULL, fd_rt, s * G + j);
 #pragma unroll
-                        for (int k = 0; k < R; ++k) {
-                            const int row = lane + 32 * k;
-                            T Jr[N];
+                            for (int i = 0; i < N; ++i) pp[i] = (i == j) ? xpm : p[i];
+                        } else {
 #pragma unroll
-                            for (int i = 0; i < N; ++i) Jr[i] = (T)0;
-                            if (row < m) Model::jacobian(pre, p, row, tk[k], Jr);
+                            for (int i = 0; i < N; ++i) pp[i] = p[i];
+                        }
+                        const typename Model::Pre pre = Model::prepare(pp);
+                        bool generic = true;
+                        if constexpr (kShared) {
+                            if (shared) { generic = false; Model::template fds_args<R>(it, p, tk, xpr, xmr, ea); }
+                        }
+                        if (generic) {
 #pragma unroll
-                            for (int i = 0; i < N; ++i) sm.J[s][i][row] = Jr[i];
+                            for (int r = 0; r < R; ++r) Model::exp_args(pre, pp, tk[r], ea + r * NE);
+                        }
+                        exp_repro_many_conv<KB>(ea, ee);
+                        if constexpr (kShared) {
+                            if (shared)
+                                Model::template fds_deliver<R>(it, p, yo, ee, fds, xpr, xmr, rtr, xpa, xma, rta,
+                                    [&](int col, int k, T v) { const int row = lane + 32 * k; sm.J[s][col][row] = (row < m) ? v : (T)0; });
+                        }
+                        if (generic) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {
+                                const int row = lane + 32 * r;
+                                if (!FD && !evalOnly) {                                                          // LS:1011-1015
+                                    T Jr[N];
+                                    Model::finish_j(pre, pp, tk[r], ee + r * NE, Jr);
+#pragma unroll
+                                    for (int i = 0; i < N; ++i) sm.J[s][i][row] = (row < m) ? Jr[i] : (T)0;
+                                } else {
+                                    T v;
+                                    Model::finish_r(pre, pp, tk[r], yo[r], ee + r * NE, v);
+                                    v = (row < m) ? v : (T)0;
+                                    if (evalOnly) { dst[row] = v; part += v * v; }
+                                    else if (sgn == 0) sm.J[s][j][row] = v;                                      // f(x + h e_j), parked in its column
+                                    else sm.J[s][j][row] = (rt != (T)0) ? (sm.J[s][j][row] - v) * rt : (T)0;     // LS:1040-1047
+                                }
+                            }
                         }
                     }
-                } else {                                                                                     // Broyden, LS:999-1007
+                    if (lane == s * G && evalOnly) ++sEvals;
+                    if (evalOnly) {
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(MUX_FULL, part, off);
+                        if (grp == s) trial = part;
+                    }
+                }
+
+                if (f & MUX_JAC_BROYDEN) {                                                                       // LS:999-1007
                     T dxs[N];
 #pragma unroll
-                    for (int j = 0; j < N; ++j) dxs[j] = __shfl_sync(FULLW, dX, s * G + j);
-                    const T negd = -rcp_ni(__shfl_sync(FULLW, deltaX_dot, s * G));                           // LS:1001
+                    for (int j = 0; j < N; ++j) dxs[j] = __shfl_sync(MUX_FULL, dX, s * G + j);
+                    const T negd = -rcp_ni(__shfl_sync(MUX_FULL, deltaX_dot, s * G));                            // LS:1001
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         const int row = lane + 32 * k;
@@ -540,202 +769,53 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         for (int i = 0; i < N; ++i) Jr[i] = sm.J[s][i][row];
                         T acc = (T)0;                                            // here y = f_new, mBuffer = f_old (after the swap, LS:1136)
 #pragma unroll
-                        for (int i = 0; i < N; ++i) acc = fma(Jr[i], dxs[i], acc);                           // gemv(1, J, deltaX, 1, mBuffer)
-                        const T v = ((slot_get(mb, s, k) - slot_get(yv, s, k)) + acc) * negd;                // axpy(-1, y, mBuffer); scal(-d, mBuffer)
+                        for (int i = 0; i < N; ++i) acc = fma(Jr[i], dxs[i], acc);                               // gemv(1, J, deltaX, 1, mBuffer)
+                        const T v = ((mv[row] - yv[row]) + acc) * negd;                                          // axpy(-1, y, mBuffer); scal(-d, mBuffer)
+                        if (row < m) {
 #pragma unroll
-                        for (int i = 0; i < N; ++i) sm.J[s][i][row] = fma(v, dxs[i], Jr[i]);                 // ger(1, mBuffer, deltaX, J)
-                    }
-                }
-                T ys[R];
-#pragma unroll
-                for (int k = 0; k < R; ++k) ys[k] = slot_get(yv, s, k);
-                // J^T y (LS:1052) and J^T J (syrk, LS:1065): MUX_RED of the K values at a time -- my rows' partial sums, one
-                // padded shared-memory row per value, lane v adds the 32 partials of value v in a fixed order
-#pragma unroll
-                for (int c0 = 0; c0 < K; c0 += MUX_RED) {
-                    T part[MUX_RED];
-#pragma unroll
-                    for (int e = 0; e < MUX_RED; ++e) part[e] = (T)0;
-#pragma unroll
-                    for (int k = 0; k < R; ++k) {
-                        const int row = lane + 32 * k;
-                        T Jr[N];
-#pragma unroll
-                        for (int i = 0; i < N; ++i) Jr[i] = sm.J[s][i][row];
-#pragma unroll
-                        for (int e = 0; e < MUX_RED; ++e) {
-                            const int v = c0 + e;
-                            if (v < NP) { const int i = untri_row(v), j = v - i * (i + 1) / 2; part[e] = fma(Jr[i], Jr[j], part[e]); }
-                            else if (v < K) part[e] = fma(Jr[v - NP], ys[k], part[e]);
+                            for (int i = 0; i < N; ++i) sm.J[s][i][row] = fma(v, dxs[i], Jr[i]);                 // ger(1, mBuffer, deltaX, J)
                         }
                     }
+                }
+
+                if (f & (MUX_JAC_FRESH | MUX_JAC_BROYDEN)) {
+                    // J^T y (LS:1052) and J^T J (syrk, LS:1065) on the FP64 tensor pipe.  m8n8k4: A = J^T (8 parameters x 4 rows),
+                    // lane holds A[lane / 4][lane % 4]; B = J (4 rows x 8 parameters), lane holds B[lane % 4][lane / 4] -- the same
+                    // value.  Four independent accumulator sets (rows 4q..4q+3 go to set q % 4), summed in a fixed order.
                     __syncwarp();
+                    const int pi = lane >> 2, kk = lane & 3;
+                    const T* const Ji = sm.J[s][pi];
+                    double c[4][2], jy4[4];
 #pragma unroll
-                    for (int e = 0; e < MUX_RED; ++e) if (c0 + e < K) sm.red[e][lane] = part[e];
-                    __syncwarp();
-                    if (lane < MUX_RED && c0 + lane < K) {
-                        const T* rr = sm.red[lane];
-                        T s0 = (T)0, s1 = (T)0, s2 = (T)0, s3 = (T)0;
+                    for (int a = 0; a < 4; ++a) { c[a][0] = 0.0; c[a][1] = 0.0; jy4[a] = 0.0; }
+                    const int nq = (m + 15) >> 4;
+#pragma unroll 1
+                    for (int q = 0; q < nq; ++q) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) { s0 += rr[i]; s1 += rr[i + 1]; s2 += rr[i + 2]; s3 += rr[i + 3]; }
-                        const T tot = (s0 + s1) + (s2 + s3);
-                        const int v = c0 + lane;
-                        if (v < NP) { const int i = untri_row(v), j = v - i * (i + 1) / 2; sm.JJ[s][i * G + j] = tot; sm.JJ[s][j * G + i] = tot; }
-                        else sm.Jy[s][v - NP] = tot;
+                        for (int a = 0; a < 4; ++a) {
+                            const double av = (double)Ji[16 * q + 4 * a + kk];
+                            const double yy = (double)yv[16 * q + 4 * a + kk];
+                            mux_dmma884(c[a], av, av);
+                            jy4[a] = fma(av, yy, jy4[a]);
+                        }
                     }
+                    const double c0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
+                    const double c1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+                    double jy = (jy4[0] + jy4[1]) + (jy4[2] + jy4[3]);
+                    jy += __shfl_xor_sync(MUX_FULL, jy, 1);
+                    jy += __shfl_xor_sync(MUX_FULL, jy, 2);
+                    // lane holds (J^T J)[pi][2 kk], [pi][2 kk + 1]; the lower triangle is mirrored so the matrix is exactly symmetric
+                    const int j0 = 2 * kk, j1 = 2 * kk + 1;
+                    if (j0 <= pi) { sm.JJ[s][pi * G + j0] = (T)c0; sm.JJ[s][j0 * G + pi] = (T)c0; }
+                    if (j1 <= pi) { sm.JJ[s][pi * G + j1] = (T)c1; sm.JJ[s][j1 * G + pi] = (T)c1; }
+                    if (kk == 0) sm.Jy[s][pi] = (T)jy;
                 }
                 __syncwarp();
             }
-        }
-        __syncwarp();
-
-        // =============================================================== phase 2 (groups): g-test LS:1053-1062, lambda LS:1067-1072, BOXCQP LS:1074-1085, trial point LS:1087-1112
-        if (active && !finished && !init) {
-            if (jacMode != MUX_JAC_NONE) {
-                Jy = valid ? sm.Jy[grp][gl] : (T)0;
-                T gsel = gmax8(gmask, t_abs(Jy));                  // iamax picks the first max |.|: its magnitude is the max
-                const T j0 = gshfl(gmask, Jy, 0);
-                if (!(j0 == j0)) gsel = j0;                        // BLAS: a NaN wins iamax only as the first element
-                if (!(gsel > st.gradTolerance)) {
-                    if (age == 0) { status = mir_ls_gConverged; finished = true; }
-                    else { age = maxAge; skipRest = true; }
-                }
-            }
-            if (!finished && !skipRest) {
-                T JJrow[G];
-                T JJdiag = (T)0;
-#pragma unroll
-                for (int j = 0; j < G; ++j) { JJrow[j] = sm.JJ[grp][gl * G + j]; JJdiag = (j == gl) ? JJrow[j] : JJdiag; }
-                if (!(lambda >= st.minLambda)) {                                                             // LS:1067-1072
-                    const T dmax = gmax8(gmask, valid ? JJdiag : (T)0);   // diag[iamax]; the diagonal of J^T J is >= 0
-                    lambda = (T)(0.001 * (double)dmax);
-                    if (!(lambda >= st.minLambda)) lambda = (T)1;
-                }
-                QPCounters qc{0, 0};
-                const int qps = boxqp_dist<T, N>(gmask, gl, gshift, st.qpSettings, JJrow, lambda, Jy, lo - x, up - x, dX, qc);   // LS:1074-1080
-                sSolves += qc.solves; sQPIt += qc.iterations;
-                const bool nan = __any_sync(gmask, valid && !(dX <= dX));                                    // LS:1087-1092
-                if (qps != mir_qp_solved || nan) { status = mir_ls_numericError; finished = true; }          // LS:1080-1092
-                else {
-                    dX = valid ? add_rn(add_rn(dX, x), -x) : (T)0;                                           // LS:1096-1097
-                    nd = gsum8(gmask, dX * dX);                                                              // LS:1099
-                    if (!(sqrt_ni(nd) < st.maxStep)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; skipRest = true; }   // LS:1101-1106
-                    else {
-                        xt = valid ? t_max(t_min(add_rn(dX, x), up), lo) : (T)0;                             // LS:1108-1110
-                        const bool same = __all_sync(gmask, !valid || ((xt == x) && (signbit(xt) == signbit(x))));
-                        ++fCalls;                                                                            // LS:1112
-                        if (same) trial = residual;           // f(xt) == y bit for bit: evaluation skipped, a rejection follows
-                        else doEval = true;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-
-        // =============================================================== phase 3 (warp): f at the trial point (LS:1113-1115) or at x (initial residual, LS:953-955)
-        {
-            const int flags = (active && !finished && doEval) ? (MUX_EVAL | (evalInit ? MUX_EVAL_INIT : 0)) : 0;
-#pragma unroll 1
-            for (int s = 0; s < S; ++s) {
-                const int f = __shfl_sync(FULLW, flags, s * G);
-                if (!(f & MUX_EVAL)) continue;
-                const bool isInit = (f & MUX_EVAL_INIT) != 0;
-                const T src = isInit ? x : xt;
-                T p[N];
-#pragma unroll
-                for (int j = 0; j < N; ++j) p[j] = __shfl_sync(FULLW, src, s * G + j);
-                const unsigned long long sprob = __shfl_sync(FULLW, prob, s * G);
-                T tk[R], yos[R], out[R];
-#pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    const int row = lane + 32 * k;
-                    tk[k] = gridPerProblem ? ((Model::kHasData && row < m) ? tptr[sprob * (unsigned long long)m + row] : (T)0) : tts[k];
-                    if (isInit) {
-                        const T v = (Model::kHasData && row < m) ? yptr[sprob * (unsigned long long)m + row] : (T)0;
-                        slot_put(yo, s, k, v);
-                        yos[k] = v;
-                    } else yos[k] = slot_get(yo, s, k);
-                }
-                T part = eval_rows(p, tk, yos, out);
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULLW, part, off);
-#pragma unroll
-                for (int k = 0; k < R; ++k) { if (isInit) slot_put(yv, s, k, out[k]); else slot_put(mb, s, k, out[k]); }
-                if (grp == s) trial = part;
-                if (lane == s * G) ++sEvals;
-            }
-        }
-        __syncwarp();
-
-        // =============================================================== phase 4 (groups): accept / reject, gain ratio, lambda, convergence, LS:1117-1175
-        if (active && !finished) {
-            if (init) {                                                                                      // LS:953-971
-                init = false;
-                residual = trial; fCalls = 1;
-                fConverged = residual <= st.maxGoodResidual;
-                needJacobian = true; age = maxAge;
-            } else {
-                if (!skipRest) {
-                    if (!(trial <= Num<T>::inf())) { status = mir_ls_numericError; finished = true; }        // LS:1117-1122
-                    else {
-                        const T improvement = residual - trial;                                              // LS:1124
-                        if (!(improvement > (T)0)) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; }         // LS:1125-1130
-                        else {
-                            accepted = true;
-                            needJacobian = true; mu = (T)1; ++iterations; ++sAccepted;                       // LS:1132-1139
-                            x = xt;
-                            residual = trial;
-                            fConverged = residual <= st.maxGoodResidual;
-                            deltaX_dot = nd;
-                            T acc = (T)0;                                                                    // symv(Lower, 1, JJ, deltaX, 2, Jy), LS:1141
-#pragma unroll
-                            for (int j = 0; j < G; ++j) acc = fma(sm.JJ[grp][gl * G + j], gshfl(gmask, dX, j), acc);
-                            Jy = acc + (T)2 * Jy;                      // (scratch from here, as in the reference)
-                            const T pred = -gsum8(gmask, Jy * dX);                                           // LS:1142
-                            if (!(pred > (T)0)) { status = mir_ls_furtherImprovement; finished = true; }     // LS:1144-1148
-                            else {
-                                const T rho = div_ni(pred, improvement);                                     // LS:1150
-                                if (rho < st.minStepQuality) { lambda *= st.lambdaIncrease * mu; mu *= (T)2; }   // LS:1152-1156
-                                else if (rho >= st.goodStepQuality) lambda = t_max(st.lambdaDecrease * lambda * mu, st.minLambda);   // LS:1158-1161
-                                const T xmax = gmax8(gmask, valid ? t_abs(x) : (T)0);                        // LS:1164 (nrm2, scaled)
-                                T xn = (T)0;
-                                if (xmax > (T)0) {
-                                    const T vx = valid ? x * rcp_ni(xmax) : (T)0;
-                                    xn = xmax * sqrt_ni(gsum8(gmask, vx * vx));
-                                }
-                                const T sd = sqrt_ni(deltaX_dot);
-                                if (!(sd > st.absTolerance && xn > sd * st.relTolerance)) {                  // LS:1164-1173
-                                    if (age == 0) { status = mir_ls_xConverged; finished = true; }
-                                    else age = maxAge;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (!finished && !(iterations < st.maxIterations)) { status = mir_ls_maxIterations; finished = true; }   // LS:1175
-            }
-        }
-        if (active && finished) {
-            if (valid) static_cast<T*>(args.x)[prob * N + gl] = x;
-            if (gl == 0) {
-                Result ret;
-                ret.status = status; ret.iterations = iterations; ret.fCalls = fCalls; ret.gCalls = gCalls;
-                ret.residual = residual; ret.lambda = lambda;
-                static_cast<Result*>(args.results)[prob] = ret;
-            }
-            active = false;
-        }
-        __syncwarp();
-        // accepted steps: mBuffer becomes y (the reference swaps the slices, LS:1136) -- on every lane, they all hold rows
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            if (__shfl_sync(FULLW, accepted ? 1 : 0, s * G)) {
-#pragma unroll
-                for (int k = 0; k < R; ++k) { const T tmp = mb[s][k]; mb[s][k] = yv[s][k]; yv[s][k] = tmp; }
-            }
+            if constexpr (MUX_WARPS > 1) __syncthreads(); else __syncwarp();
         }
     }
-
+done:
     if (args.stats && gl == 0 && sProblems) {
         atomicAdd((unsigned long long*)&args.stats->problems, (unsigned long long)sProblems);
         atomicAdd((unsigned long long*)&args.stats->passes, (unsigned long long)sPasses);

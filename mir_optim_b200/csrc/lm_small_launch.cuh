@@ -78,23 +78,38 @@ int launch_tpp(const typename Num<T>::Settings& st, const SmallBatchArgs& args, 
     return (args.flags & MIR_MODEL_FD_JACOBIAN) ? launch_tpp_fd<Model, T, true>(st, args, stream) : launch_tpp_fd<Model, T, false>(st, args, stream);
 }
 
-// Four problems per warp (lm_mux.cuh): n <= 8, m <= 128.
-template <class Model, class T, bool FD>
-int launch_mux_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+// Four problems per warp (lm_mux.cuh): n <= 8, m <= 128.  One warp per CTA; the warp's four problems live in its shared memory.
+template <class Model, class T, bool FD, int MUX_WARPS>
+int launch_mux_w(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
-    auto kern = lm_mux_kernel<Model, T, FD>;
+    auto kern = lm_mux_kernel<Model, T, FD, MUX_WARPS>;
     const size_t smem = sizeof(MuxWarpSmem<T>) * MUX_WARPS;
-    MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attrSet = false;       // (per instantiation)
+    if (!attrSet) {
+        MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attrSet = true;
+    }
     int blocksPerSM = 0;
-    MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, MUX_WARPS * 32, smem));
+    MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, 32 * MUX_WARPS, smem));
     if (blocksPerSM < 1) blocksPerSM = 1;
-    const unsigned long long perBlock = (unsigned long long)MUX_WARPS * MUX_SLOTS;
+    const unsigned long long perBlock = (unsigned long long)MUX_SLOTS * MUX_WARPS;
     unsigned long long blocksWanted = (args.batch + perBlock - 1) / perBlock;
     unsigned long long grid = (unsigned long long)sm_count() * blocksPerSM;      // persistent: one resident wave
     if (blocksWanted < grid) grid = blocksWanted ? blocksWanted : 1;
-    kern<<<(unsigned)grid, MUX_WARPS * 32, smem, stream>>>(st, args);
+    kern<<<(unsigned)grid, 32 * MUX_WARPS, smem, stream>>>(st, args);
     count_launch();
     return check_cuda(cudaGetLastError(), "lm_mux_kernel launch");
+}
+// Warps per CTA: as many as the shared memory of one SM holds (5 in double, 10 in float), stepping through the phases
+// together (lm_mux.cuh); MIRB200_MUX_LOCKSTEP=0 launches free-running single-warp CTAs instead (experiments).
+template <class Model, class T, bool FD>
+int launch_mux_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
+{
+    static const bool lockstep = [] { const char* e = std::getenv("MIRB200_MUX_LOCKSTEP"); return !(e && *e == '0'); }();
+    constexpr int W = sizeof(T) == 8 ? 5 : 10;
+    if (lockstep && args.batch >= (unsigned long long)MUX_SLOTS * W * 2) return launch_mux_w<Model, T, FD, W>(st, args, stream);
+    return launch_mux_w<Model, T, FD, 1>(st, args, stream);
 }
 template <class Model, class T>
 int launch_mux(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)

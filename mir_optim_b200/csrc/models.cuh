@@ -73,6 +73,9 @@ template <class T> struct ModelSqrtCircle {
 // finish_rj (residual and/or Jacobian row from the NE exp values).  residual(), jacobian() and residual_jacobian()
 // are defined through the same pieces, so every path performs the same operations in the same order.
 template <class M, class T, bool INL> struct ExpModelBase {
+    // true: the model provides fd_shared(), a finite-difference Jacobian that reuses the sub-expressions its 2n
+    // evaluations have in common (lm_mux.cuh); false: the kernels evaluate the residual 2n times
+    static constexpr bool kFDShared = false;
     template <class P, int NN> __device__ static T residual(const P& q, const T (&p)[NN], int, T t, T y) {
         T a[M::NE], e[M::NE], r;
         M::exp_args(q, p, t, a);
@@ -177,6 +180,70 @@ template <class T, int N_, bool INL = false> struct ModelSumExp : ExpModelBase<M
     __device__ static void finish_j(const Pre&, const T (&p)[N], T t, const T* e, T (&J)[N]) {
 #pragma unroll
         for (int k = 0; k < N; k += 2) { J[k] = e[k / 2]; J[k + 1] = mul_rn(-mul_rn(p[k], t), e[k / 2]); }
+    }
+
+    // ---- finite-difference Jacobian with shared exponentials (lm_mux.cuh) -------------------------------------------
+    // The central difference of least_squares.d:1018-1049 evaluates f at x + h e_j and x - h e_j for every parameter j.
+    // Perturbing the amplitude p[2k] changes no exponential, perturbing the rate p[2k+1] changes one: the others have the
+    // same argument mul_rn(-p[2k'+1], t), hence the same bits, in all 2n evaluations.  They are computed once (the
+    // "base" item) and every perturbed residual is re-summed from them with the operations of finish_r in the same
+    // order, so each Jacobian entry is bit-identical to the one obtained from 2n full evaluations -- with 3 NE instead
+    // of 4 NE^2 exponentials per row.  Work is cut into items of KB = R NE exponentials (R = 4 rows per lane):
+    //   item 0                 base: the NE exps of the R rows at p
+    //   items 1 .. NE / CPI    CPI = NE / 2 components each: exp(-(b_k + h) t) and exp(-(b_k - h) t) for the R rows;
+    //                          delivers the columns 2k and 2k+1 of those components
+    static constexpr bool kFDShared = (NE == 2 || NE == 4);
+    static constexpr int CPI = NE / 2;
+    template <int R> struct FDState { T eb[R][NE]; };
+    template <int R>
+    __device__ static void fds_args(int it, const T (&p)[N], const T (&tk)[R], const T* xp, const T* xm, T* ea) {
+        if (it == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int k = 0; k < NE; ++k) ea[r * NE + k] = mul_rn(-p[2 * k + 1], tk[r]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPI; ++c)
+#pragma unroll
+                for (int r = 0; r < R; ++r) { ea[c * 2 * R + r] = mul_rn(-xp[c], tk[r]); ea[c * 2 * R + R + r] = mul_rn(-xm[c], tk[r]); }
+        }
+    }
+    // xpr / xmr / rtr [c]: x + h, x - h and 1 / (2h) of the rate p[2k+1] of component k = (it - 1) CPI + c; xpa / xma / rta:
+    // of its amplitude p[2k] (rt == 0 marks a column that the reference sets to zero, LS:1045-1047).
+    // put(j, r, v): J[row r of this lane][j] = v.
+    template <int R, class PUT>
+    __device__ static void fds_deliver(int it, const T (&p)[N], const T (&yo)[R], const T* ee, FDState<R>& st,
+                                       const T* xpr, const T* xmr, const T* rtr, const T* xpa, const T* xma, const T* rta, PUT put) {
+        (void)xpr; (void)xmr;
+        if (it == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int k = 0; k < NE; ++k) st.eb[r][k] = ee[r * NE + k];
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPI; ++c) {
+                const int kc = (it - 1) * CPI + c;
+                auto resum = [&](int r, T amp, T enew, bool newAmp, bool newExp) -> T {
+                    T acc = (T)0;
+#pragma unroll
+                    for (int k = 0; k < NE; ++k) {
+                        const T a = (newAmp && k == kc) ? amp : p[2 * k];
+                        const T e = (newExp && k == kc) ? enew : st.eb[r][k];
+                        acc = add_rn(acc, mul_rn(a, e));
+                    }
+                    return sub_rn(acc, yo[r]);
+                };
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const T fpr = resum(r, (T)0, ee[c * 2 * R + r], false, true), fmr = resum(r, (T)0, ee[c * 2 * R + R + r], false, true);
+                    put(2 * kc + 1, r, (rtr[c] != (T)0) ? (fpr - fmr) * rtr[c] : (T)0);
+                    const T fpa = resum(r, xpa[c], (T)0, true, false), fma_ = resum(r, xma[c], (T)0, true, false);
+                    put(2 * kc, r, (rta[c] != (T)0) ? (fpa - fma_) * rta[c] : (T)0);
+                }
+            }
+        }
     }
 };
 

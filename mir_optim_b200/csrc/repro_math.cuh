@@ -70,6 +70,44 @@ static __device__ __forceinline__ void exp_repro_many(const double* __restrict__
     }
 }
 
+// Warp-convergent variant (all 32 lanes must call it together): same value for every input, but the scaling p * 2^k is
+// an integer add on the exponent field when every argument of the warp is in [-700, 700] -- the result is then a normal
+// number and both exact power-of-two products of the general path reduce to that add.  Anything else (huge arguments,
+// NaN) sends the whole warp through the general path.  20 instead of 33 instructions per exponential.
+template <int K>
+static __device__ __forceinline__ void exp_repro_many_conv(const double* __restrict__ x, double* __restrict__ e)
+{
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) ok = ok && (fabs(x[j]) < 700.0);
+    if (__all_sync(0xffffffffu, ok)) {
+        double k[K], r[K], p[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) k[j] = rint(__dmul_rn(x[j], kExpD[0]));
+#pragma unroll
+        for (int j = 0; j < K; ++j) r[j] = fma(-k[j], kExpD[1], x[j]);
+#pragma unroll
+        for (int j = 0; j < K; ++j) r[j] = fma(-k[j], kExpD[2], r[j]);
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = kExpD[3];
+#pragma unroll
+        for (int i = 4; i < 17; ++i) {
+            const double c = kExpD[i];
+#pragma unroll
+            for (int j = 0; j < K; ++j) p[j] = fma(p[j], r[j], c);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int ki = __double2int_rn(k[j]);
+            e[j] = __hiloint2double(__double2hiint(p[j]) + (ki << 20), __double2loint(p[j]));
+        }
+    } else {
+        exp_repro_many<K>(x, e);
+    }
+}
+template <int K>
+static __device__ __forceinline__ void exp_repro_many_conv(const float* __restrict__ x, float* __restrict__ e);
+
 template <int K>
 static __device__ __forceinline__ void exp_repro_many(const float* __restrict__ x, float* __restrict__ e)
 {
@@ -96,6 +134,35 @@ static __device__ __forceinline__ void exp_repro_many(const float* __restrict__ 
         float v = __fmul_rn(__fmul_rn(p[j], s1), s2);
         v = (x[j] > 88.72284f) ? Num<float>::inf() : v;
         e[j] = (x[j] > -104.0f) ? v : ((x[j] == x[j]) ? 0.0f : x[j]);
+    }
+}
+
+template <int K>
+static __device__ __forceinline__ void exp_repro_many_conv(const float* __restrict__ x, float* __restrict__ e)
+{
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) ok = ok && (fabsf(x[j]) < 80.0f);
+    if (__all_sync(0xffffffffu, ok)) {
+        float k[K], r[K], p[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) k[j] = rintf(__fmul_rn(x[j], kExpS[0]));
+#pragma unroll
+        for (int j = 0; j < K; ++j) r[j] = fmaf(-k[j], kExpS[1], x[j]);
+#pragma unroll
+        for (int j = 0; j < K; ++j) r[j] = fmaf(-k[j], kExpS[2], r[j]);
+#pragma unroll
+        for (int j = 0; j < K; ++j) p[j] = kExpS[3];
+#pragma unroll
+        for (int i = 4; i < 11; ++i) {
+            const float c = kExpS[i];
+#pragma unroll
+            for (int j = 0; j < K; ++j) p[j] = fmaf(p[j], r[j], c);
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) e[j] = __int_as_float(__float_as_int(p[j]) + (__float2int_rn(k[j]) << 23));
+    } else {
+        exp_repro_many<K>(x, e);
     }
 }
 

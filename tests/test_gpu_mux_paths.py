@@ -86,7 +86,10 @@ def test_active_bounds_n8(eng, oracle_lib):
 
     def mut(s): pass
     xg, rg, xo, ro, stats = both(eng, oracle_lib, wl, mut, False, l=l, u=u)
-    assert np.all(rg["status"] >= -1)
+    # (BOXCQP's all-variables-free exit, BQ:265-266 -> LS:1080-1085 numericError, is the reference's behaviour on a share of
+    # these problems: the kernel has to reproduce it, not avoid it)
+    assert np.mean(rg["status"] == ro["status"]) > 0.97
+    assert np.mean(same_counters(rg, ro)) > 0.9
     onb_g = (xg == l) | (xg == u); onb_o = (xo == l) | (xo == u)
     assert onb_o.any(axis=1).mean() > 0.9
     assert np.mean(np.all(onb_g == onb_o, axis=1)) > 0.97                      # same active set at the solution
