@@ -145,7 +145,7 @@ def secondary_batched(torch, eng, dev, workloads, rank):
     device-resident throughput of THIS rank's GPU (the batched paths shard without communication)."""
     out = {}
     for name, dt in (("c3_sumexp8_f64", np.float64), ("c3_sumexp8_f32", np.float32)):
-        B = 65536
+        B = 1 << 20                    # BASELINE configs[2]: 1M fits
         wl = workloads.c3_sumexp8(B, dtype=dt, seed=3 + rank)
         st = eng.settings(dt)
         T = lambda v: torch.from_numpy(v).to(dev)

@@ -9,7 +9,8 @@
 //
 //   * ROW phases (residual evaluation, finite-difference / analytic Jacobian, Broyden update LS:999-1006, J^T y and
 //     J^T J, LS:1052, 1065) are WARP-cooperative: all 32 lanes work on ONE slot at a time, lane L owning rows L, L+32,
-//     L+64, L+96.  A warp does exactly the row work its problems ask for.  Jacobian, current and trial residuals live
+//     L+64, L+96.  The slots of a CTA post their row requests into a shared-memory queue and the CTA's warps pull
+//     them one by one, whichever slot they belong to: the row work of a pass is spread evenly over the warps.  Jacobian, current and trial residuals live
 //     in shared memory ([parameter][row], pitch 132: conflict-free for the row accesses, the column writes of the finite
 //     differences and the tensor-core fragment loads); the observations are re-read from global memory (L2) per evaluation.
 //     J^T J runs on the FP64 TENSOR pipe: mma.sync.m8n8k4.f64 (DMMA) takes J^T (8 x 4 rows) as A and the same values as B,
@@ -51,11 +52,24 @@ constexpr unsigned MUX_FULL = 0xffffffffu;
 // (template parameter MUX_WARPS of the kernel)
 enum { MUX_EVAL_INIT = 1, MUX_EVAL_TRIAL = 2, MUX_JAC_FRESH = 4, MUX_JAC_BROYDEN = 8 };
 
-template <class T> struct MuxWarpSmem {
-    T J[MUX_SLOTS][MUX_G][MUX_JP];      // Jacobian of each slot, [parameter][row]; parameters >= n and rows >= m stay zero
-    T vec[MUX_SLOTS][2][MUX_MMAX];      // y (current residuals) and mBuffer (trial / previous residuals); `ysel` says which is which
-    T JJ[MUX_SLOTS][MUX_G * MUX_G];     // J^T J, full symmetric storage, undamped
-    T Jy[MUX_SLOTS][MUX_G];             // J^T y
+// Everything a problem ("slot") keeps between phases, in shared memory of its CTA.
+template <class T> struct MuxSlot {
+    T J[MUX_G][MUX_JP];                 // Jacobian, [parameter][row]; parameters >= n and rows >= m stay zero
+    T vec[2][MUX_MMAX];                 // y (current residuals) and mBuffer (trial / previous residuals); `ysel` says which is which
+    T JJ[MUX_G * MUX_G];                // J^T J, full symmetric storage, undamped
+    T Jy[MUX_G];                        // J^T y
+    // row-task mailbox: written by the slot's group before a row phase, read by whichever warp takes the task
+    T p[MUX_G];                         // the point to evaluate at (trial point or x)
+    T dX[MUX_G];                        // accepted step (Broyden)
+    T fxp[MUX_G], fxm[MUX_G], frt[MUX_G];   // finite differences: x + h, x - h, 1 / (2h) per parameter
+    T ddot, result;                     // |dX|^2; ||r||^2 of the evaluation (written by the row phase)
+    unsigned long long prob;
+    int flags, ysel;
+};
+template <class T, int W> struct MuxCtaSmem {
+    MuxSlot<T> slot[MUX_SLOTS * W];
+    int qn[2], qhead[2];                // row-task queues of the two halves of the pass loop: length, next task
+    unsigned char qtask[2][MUX_SLOTS * W];
 };
 
 // ---- group (8-lane) collectives, executed by the whole warp; every lane of a group receives the same bits -----------
@@ -365,7 +379,8 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
     constexpr bool kShared = FD && Model::kFDShared;
     using Result = typename Num<T>::Result;
     extern __shared__ __align__(16) unsigned char mux_smem_raw[];
-    MuxWarpSmem<T>& sm = reinterpret_cast<MuxWarpSmem<T>*>(mux_smem_raw)[threadIdx.x >> 5];
+    using Cta = MuxCtaSmem<T, MUX_WARPS>;
+    Cta& cta = *reinterpret_cast<Cta*>(mux_smem_raw);
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3, gl = lane & 7, gshift = grp * 8;
     const bool valid = gl < N;
@@ -375,8 +390,10 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
     const T* __restrict__ tptr = static_cast<const T*>(args.t);
     const T* __restrict__ yptr = static_cast<const T*>(args.y);
 
-    for (int e = lane; e < (int)(sizeof(MuxWarpSmem<T>) / sizeof(T)); e += 32) reinterpret_cast<T*>(&sm)[e] = (T)0;
-    __syncwarp();
+    const int myslot = (threadIdx.x >> 5) * S + grp;
+    MuxSlot<T>& my = cta.slot[myslot];                                       // the slot of this lane's group
+    for (int e = threadIdx.x; e < (int)(sizeof(Cta) / 4); e += 32 * MUX_WARPS) reinterpret_cast<unsigned*>(&cta)[e] = 0u;
+    if constexpr (MUX_WARPS > 1) __syncthreads(); else __syncwarp();
 
     // ---- warp-role state: the shared abscissa of my rows (lane + 32 k)
     T tts[R];
@@ -415,7 +432,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                 if (__any_sync(MUX_FULL, accepted)) {
                     T acc = (T)0;                                                                            // symv(Lower, 1, JJ, deltaX, 2, Jy), LS:1141
 #pragma unroll
-                    for (int j = 0; j < G; ++j) acc = fma(sm.JJ[grp][gl * G + j], gshfl(dX, j), acc);
+                    for (int j = 0; j < G; ++j) acc = fma(my.JJ[gl * G + j], gshfl(dX, j), acc);
                     const T Jy2 = acc + (T)2 * Jy;
                     const T pred = -gsum8(Jy2 * dX);                                                         // LS:1142
                     T xss = gsum8(valid ? xt * xt : (T)0);                                                   // LS:1164: nrm2(x)
@@ -474,7 +491,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                     if (__any_sync(MUX_FULL, wantTail && small && !strict && inside)) {                          // tail_bounds_certificate
                         T row = (T)0;
 #pragma unroll
-                        for (int j = 0; j < G; ++j) row += t_abs(sm.JJ[grp][gl * G + j]);
+                        for (int j = 0; j < G; ++j) row += t_abs(my.JJ[gl * G + j]);
                         const T nu = gmax8(row), qinf = gmax8(t_abs(Jy));
                         const T thr = ((T)8 * nu) * (qinf / lambda), dmax = xmin * (Num<T>::lapack_eps() * (T)0.25);
                         const T ql = lo - x, qu = up - x;
@@ -579,8 +596,6 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         }
                     }
                 }
-                if constexpr (MUX_WARPS == 1) { if (__all_sync(MUX_FULL, retired)) goto done; }
-                else { if (__syncthreads_and(retired)) goto done; }
             } else {
                 // ======================================================= the initial residual has arrived, LS:953-971
                 bool go = active && !finished && passOpen;
@@ -593,7 +608,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                 // ======================================================= g-test LS:1053-1062
                 const bool jacd = go && jacMode != 0;
                 if (__any_sync(MUX_FULL, jacd)) {
-                    const T jyn = valid ? sm.Jy[grp][gl] : (T)0;
+                    const T jyn = valid ? my.Jy[gl] : (T)0;
                     T gsel = gmax8(t_abs(jyn));                    // iamax picks the first max |.|: its magnitude is the max
                     const T j0 = gshfl(jyn, 0);
                     if (!(j0 == j0)) gsel = j0;                    // BLAS: a NaN wins iamax only as the first element
@@ -611,7 +626,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                     T JJrow[G];
                     T JJdiag = (T)0;
 #pragma unroll
-                    for (int j = 0; j < G; ++j) { JJrow[j] = sm.JJ[grp][gl * G + j]; JJdiag = (j == gl) ? JJrow[j] : JJdiag; }
+                    for (int j = 0; j < G; ++j) { JJrow[j] = my.JJ[gl * G + j]; JJdiag = (j == gl) ? JJrow[j] : JJdiag; }
                     const T dmax = gmax8(valid ? JJdiag : (T)0);          // diag[iamax]; the diagonal of J^T J is >= 0
                     if (go && !(lambda >= st.minLambda)) {                                                       // LS:1067-1072
                         lambda = (T)(0.001 * (double)dmax);
@@ -643,23 +658,43 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                 }
             }
 
-            // =========================================================== row phase (warp): the slots' requests, one slot at a time
-            if constexpr (MUX_WARPS > 1) { if (half == 1) __syncthreads(); }
+            // =========================================================== row phase: post this slot's request, then pull tasks
+            bool evalPending = false;
+            if (rf != 0) {
+                my.p[gl] = (rf & MUX_EVAL_TRIAL) ? xt : x;
+                if (rf & MUX_JAC_BROYDEN) my.dX[gl] = dX;
+                if (FD && (rf & MUX_JAC_FRESH)) { my.fxp[gl] = fd_xp; my.fxm[gl] = fd_xm; my.frt[gl] = fd_rt; }
+                if (gl == 0) {
+                    my.ddot = deltaX_dot; my.prob = prob; my.flags = rf; my.ysel = ysel;
+                    cta.qtask[half][atomicAdd(&cta.qn[half], 1)] = (unsigned char)myslot;
+                }
+                evalPending = (rf & (MUX_EVAL_INIT | MUX_EVAL_TRIAL)) != 0;
+            }
+            if constexpr (MUX_WARPS > 1) {
+                if (half == 0) { if (__syncthreads_and(retired)) goto done; }
+                else __syncthreads();
+            } else {
+                if (half == 0 && __all_sync(MUX_FULL, retired)) goto done;
+                __syncwarp();
+            }
+            if (threadIdx.x == 0) { cta.qn[half ^ 1] = 0; cta.qhead[half ^ 1] = 0; }     // the other half's queue is idle now
+            const int nTasks = cta.qn[half];
 #pragma unroll 1
-            for (int s = 0; s < S; ++s) {
-                const int f = __shfl_sync(MUX_FULL, rf, s * G);
-                if (f == 0) continue;
-                const unsigned long long sprob = __shfl_sync(MUX_FULL, prob, s * G);
-                const int ys = __shfl_sync(MUX_FULL, ysel, s * G);
-                T* const yv = sm.vec[s][ys];
-                T* const mv = sm.vec[s][ys ^ 1];
+            for (;;) {
+                int task = 0;
+                if (lane == 0) task = atomicAdd(&cta.qhead[half], 1);
+                task = __shfl_sync(MUX_FULL, task, 0);
+                if (task >= nTasks) break;
+                const int s = cta.qtask[half][task];
+                MuxSlot<T>& sl = cta.slot[s];
+                const int f = sl.flags;
+                const unsigned long long sprob = sl.prob;
+                T* const yv = sl.vec[sl.ysel];
+                T* const mv = sl.vec[sl.ysel ^ 1];
                 const bool evalOnly = (f & (MUX_EVAL_INIT | MUX_EVAL_TRIAL)) != 0;
                 T p[N];
-                {
-                    const T src = (f & MUX_EVAL_TRIAL) ? xt : x;
 #pragma unroll
-                    for (int j = 0; j < N; ++j) p[j] = __shfl_sync(MUX_FULL, src, s * G + j);
-                }
+                for (int j = 0; j < N; ++j) p[j] = sl.p[j];
                 T tk[R];
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
@@ -684,7 +719,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                     int nItems = (evalOnly || !FD) ? 1 : 2 * N;
                     if constexpr (kShared) { if (shared) nItems = 1 + NE / Model::CPI; }
                     [[maybe_unused]] typename SharedFD<Model, T, kShared>::State fds = {};
-                    if (lane == s * G && !evalOnly && FD) sEvals += 2u * N;
+                    if (lane == 0 && !evalOnly && FD) sEvals += 2u * N;
 #pragma unroll 1
                     for (int it = 0; it < nItems; ++it) {
                         const int j = it >> 1, sgn = it & 1;
@@ -697,16 +732,16 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
 #pragma unroll
                                 for (int c = 0; c < CPI; ++c) {
                                     const int kc = (it >= 1) ? (it - 1) * CPI + c : 0;
-                                    xpr[c] = __shfl_sync(MUX_FULL, fd_xp, s * G + 2 * kc + 1); xmr[c] = __shfl_sync(MUX_FULL, fd_xm, s * G + 2 * kc + 1);
-                                    rtr[c] = __shfl_sync(MUX_FULL, fd_rt, s * G + 2 * kc + 1);
-                                    xpa[c] = __shfl_sync(MUX_FULL, fd_xp, s * G + 2 * kc); xma[c] = __shfl_sync(MUX_FULL, fd_xm, s * G + 2 * kc);
-                                    rta[c] = __shfl_sync(MUX_FULL, fd_rt, s * G + 2 * kc);
+                                    xpr[c] = sl.fxp[2 * kc + 1]; xmr[c] = sl.fxm[2 * kc + 1];
+                                    rtr[c] = sl.frt[2 * kc + 1];
+                                    xpa[c] = sl.fxp[2 * kc]; xma[c] = sl.fxm[2 * kc];
+                                    rta[c] = sl.frt[2 * kc];
                                 }
                             }
                         }
                         if (FD && !evalOnly && !kShared) {
-                            const T xpm = __shfl_sync(MUX_FULL, sgn ? fd_xm : fd_xp, s * G + j);
-                            rt = __shfl_sync(MUX_FULL, fd_rt, s * G + j);
+                            const T xpm = sgn ? sl.fxm[j] : sl.fxp[j];
+                            rt = sl.frt[j];
 #pragma unroll
                             for (int i = 0; i < N; ++i) pp[i] = (i == j) ? xpm : p[i];
                         } else {
@@ -726,7 +761,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                         if constexpr (kShared) {
                             if (shared)
                                 Model::template fds_deliver<R>(it, p, yo, ee, fds, xpr, xmr, rtr, xpa, xma, rta,
-                                    [&](int col, int k, T v) { const int row = lane + 32 * k; sm.J[s][col][row] = (row < m) ? v : (T)0; });
+                                    [&](int col, int k, T v) { const int row = lane + 32 * k; sl.J[col][row] = (row < m) ? v : (T)0; });
                         }
                         if (generic) {
 #pragma unroll
@@ -736,44 +771,44 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                                     T Jr[N];
                                     Model::finish_j(pre, pp, tk[r], ee + r * NE, Jr);
 #pragma unroll
-                                    for (int i = 0; i < N; ++i) sm.J[s][i][row] = (row < m) ? Jr[i] : (T)0;
+                                    for (int i = 0; i < N; ++i) sl.J[i][row] = (row < m) ? Jr[i] : (T)0;
                                 } else {
                                     T v;
                                     Model::finish_r(pre, pp, tk[r], yo[r], ee + r * NE, v);
                                     v = (row < m) ? v : (T)0;
                                     if (evalOnly) { dst[row] = v; part += v * v; }
-                                    else if (sgn == 0) sm.J[s][j][row] = v;                                      // f(x + h e_j), parked in its column
-                                    else sm.J[s][j][row] = (rt != (T)0) ? (sm.J[s][j][row] - v) * rt : (T)0;     // LS:1040-1047
+                                    else if (sgn == 0) sl.J[j][row] = v;                                      // f(x + h e_j), parked in its column
+                                    else sl.J[j][row] = (rt != (T)0) ? (sl.J[j][row] - v) * rt : (T)0;     // LS:1040-1047
                                 }
                             }
                         }
                     }
-                    if (lane == s * G && evalOnly) ++sEvals;
+                    if (lane == 0 && evalOnly) ++sEvals;
                     if (evalOnly) {
 #pragma unroll
                         for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(MUX_FULL, part, off);
-                        if (grp == s) trial = part;
+                        if (lane == 0) sl.result = part;
                     }
                 }
 
                 if (f & MUX_JAC_BROYDEN) {                                                                       // LS:999-1007
                     T dxs[N];
 #pragma unroll
-                    for (int j = 0; j < N; ++j) dxs[j] = __shfl_sync(MUX_FULL, dX, s * G + j);
-                    const T negd = -rcp_ni(__shfl_sync(MUX_FULL, deltaX_dot, s * G));                            // LS:1001
+                    for (int j = 0; j < N; ++j) dxs[j] = sl.dX[j];
+                    const T negd = -rcp_ni(sl.ddot);                                                             // LS:1001
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         const int row = lane + 32 * k;
                         T Jr[N];
 #pragma unroll
-                        for (int i = 0; i < N; ++i) Jr[i] = sm.J[s][i][row];
+                        for (int i = 0; i < N; ++i) Jr[i] = sl.J[i][row];
                         T acc = (T)0;                                            // here y = f_new, mBuffer = f_old (after the swap, LS:1136)
 #pragma unroll
                         for (int i = 0; i < N; ++i) acc = fma(Jr[i], dxs[i], acc);                               // gemv(1, J, deltaX, 1, mBuffer)
                         const T v = ((mv[row] - yv[row]) + acc) * negd;                                          // axpy(-1, y, mBuffer); scal(-d, mBuffer)
                         if (row < m) {
 #pragma unroll
-                            for (int i = 0; i < N; ++i) sm.J[s][i][row] = fma(v, dxs[i], Jr[i]);                 // ger(1, mBuffer, deltaX, J)
+                            for (int i = 0; i < N; ++i) sl.J[i][row] = fma(v, dxs[i], Jr[i]);                 // ger(1, mBuffer, deltaX, J)
                         }
                     }
                 }
@@ -784,7 +819,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                     // value.  Four independent accumulator sets (rows 4q..4q+3 go to set q % 4), summed in a fixed order.
                     __syncwarp();
                     const int pi = lane >> 2, kk = lane & 3;
-                    const T* const Ji = sm.J[s][pi];
+                    const T* const Ji = sl.J[pi];
                     double c[4][2], jy4[4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) { c[a][0] = 0.0; c[a][1] = 0.0; jy4[a] = 0.0; }
@@ -806,13 +841,14 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                     jy += __shfl_xor_sync(MUX_FULL, jy, 2);
                     // lane holds (J^T J)[pi][2 kk], [pi][2 kk + 1]; the lower triangle is mirrored so the matrix is exactly symmetric
                     const int j0 = 2 * kk, j1 = 2 * kk + 1;
-                    if (j0 <= pi) { sm.JJ[s][pi * G + j0] = (T)c0; sm.JJ[s][j0 * G + pi] = (T)c0; }
-                    if (j1 <= pi) { sm.JJ[s][pi * G + j1] = (T)c1; sm.JJ[s][j1 * G + pi] = (T)c1; }
-                    if (kk == 0) sm.Jy[s][pi] = (T)jy;
+                    if (j0 <= pi) { sl.JJ[pi * G + j0] = (T)c0; sl.JJ[j0 * G + pi] = (T)c0; }
+                    if (j1 <= pi) { sl.JJ[pi * G + j1] = (T)c1; sl.JJ[j1 * G + pi] = (T)c1; }
+                    if (kk == 0) sl.Jy[pi] = (T)jy;
                 }
                 __syncwarp();
             }
             if constexpr (MUX_WARPS > 1) __syncthreads(); else __syncwarp();
+            if (evalPending) trial = my.result;
         }
     }
 done:

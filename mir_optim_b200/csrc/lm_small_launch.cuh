@@ -83,7 +83,7 @@ template <class Model, class T, bool FD, int MUX_WARPS>
 int launch_mux_w(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
     auto kern = lm_mux_kernel<Model, T, FD, MUX_WARPS>;
-    const size_t smem = sizeof(MuxWarpSmem<T>) * MUX_WARPS;
+    const size_t smem = sizeof(MuxCtaSmem<T, MUX_WARPS>);
     static bool attrSet = false;       // (per instantiation)
     if (!attrSet) {
         MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
