@@ -234,14 +234,18 @@ typedef enum mir_model_id {
     MIR_MODEL_SUMEXP        = 7,  /* r_i = sum_k p[2k] exp(-p[2k+1] t_i) - y_i       n=8  configs[2] */
     MIR_MODEL_GAUSSMIX      = 8,  /* r_i = sum_k p[3k] exp(-(t_i-p[3k+1])^2/(2 p[3k+2]^2))
                                             + p[n-2] + p[n-1] t_i - y_i   n=3K+2   configs[3] */
+    MIR_MODEL_SPLINE        = 9,  /* fitSpline's residual (fit_splie.d:58-80): p = values of a C2 cubic spline
+                                     (not-a-knot ends) at the knots `aux`; r_i = spline(t_i) - y_i, last row =
+                                     sqrt(param * integral term); n = number of knots >= 2; finite differences only */
     MIR_MODEL_COUNT_
 } mir_model_id;
 
 enum {
     MIR_MODEL_FD_JACOBIAN      = 1u,  /* g == null semantics: central differences, maxAge default 2n */
     MIR_MODEL_GRID_PER_PROBLEM = 2u,  /* t has batch*m entries instead of m shared ones              */
-    MIR_MODEL_NO_TAIL_SHORTCUT = 4u   /* verification only: execute every pass of the lambda-overflow tail
+    MIR_MODEL_NO_TAIL_SHORTCUT = 4u,  /* verification only: execute every pass of the lambda-overflow tail
                                          instead of fast-forwarding it (results are identical) */
+    MIR_MODEL_AUX_PER_PROBLEM  = 8u   /* aux has batch*n entries instead of n shared ones                   */
 };
 
 typedef struct mir_model_desc {
@@ -249,6 +253,8 @@ typedef struct mir_model_desc {
     uint32_t    flags;
     const void* t;       /* abscissa, T[m] (shared) or T[batch*m]; NULL for data-free models */
     const void* y;       /* observations, T[batch*m]; NULL for data-free models             */
+    const void* aux;     /* model constants, T[n] (shared) or T[batch*n]: the knots of MIR_MODEL_SPLINE; else NULL */
+    double      param;   /* model constant: the smoothing weight lambda of MIR_MODEL_SPLINE; else 0  */
 } mir_model_desc;
 
 /* Sentinels for the legacy entry points: pass as `f` / `g` with fContext = mir_model_desc*. */

@@ -98,7 +98,8 @@ class LSTask(C.Structure):
 
 
 class ModelDesc(C.Structure):
-    _fields_ = [("model", C.c_uint32), ("flags", C.c_uint32), ("t", C.c_void_p), ("y", C.c_void_p)]
+    _fields_ = [("model", C.c_uint32), ("flags", C.c_uint32), ("t", C.c_void_p), ("y", C.c_void_p),
+                ("aux", C.c_void_p), ("param", C.c_double)]
 
 
 class BatchStats(C.Structure):
