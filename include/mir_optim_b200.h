@@ -314,6 +314,33 @@ int mir_optimize_least_squares_batched_dev_s(
     mir_least_squares_result_s* results, mir_batch_stats* stats, void* cuda_stream);
 
 /*
+ * fitSpline (fit_splie.d:26-85): least-squares fit of a C2 cubic spline (mir.interpolate.spline with the default
+ * SplineConfiguration: not-a-knot ends) with FIXED knots x[n] to `points` data points; the unknowns are the spline
+ * values at the knots, bounded by l[n] <= spline(x) <= u[n]; lambda >= 0 weighs the smoothing term
+ * (fit_splie.d:67-80).  Exactly as the reference: start from zeros, finite-difference Jacobian, m = points +
+ * (lambda == 0) residual rows, and with lambda != 0 the smoothing row takes the place of the last point's residual.
+ *   points_x  T[points] (shared by all curves) or T[batch*points] with MIR_MODEL_GRID_PER_PROBLEM in flags
+ *   points_y  T[batch*points]
+ *   x         knots, T[n] or T[batch*n] with MIR_MODEL_AUX_PER_PROBLEM
+ *   values    T[batch*n] out: the fitted spline values at the knots (the reference returns them inside Spline!T;
+ *             its first derivatives follow from them, see mir_b200_spline_eval)
+ * Returns MIR_B200_EINVAL (message = the reference's exception text) for points < n with lambda == 0,
+ * fit_splie.d:45-49.  Host pointers; every curve is one CTA of the general batched kernel (lm_cta.cuh).
+ */
+int mir_fit_spline_d(const mir_least_squares_settings_d* settings, size_t points, const double* points_x, const double* points_y,
+                     size_t n, const double* x, const double* l, const double* u, double lambda, double* values,
+                     mir_least_squares_result_d* result);
+int mir_fit_spline_s(const mir_least_squares_settings_s* settings, size_t points, const float* points_x, const float* points_y,
+                     size_t n, const float* x, const float* l, const float* u, float lambda, float* values,
+                     mir_least_squares_result_s* result);
+int mir_fit_spline_batched_d(const mir_least_squares_settings_d* settings, size_t batch, size_t points, const double* points_x,
+                             const double* points_y, size_t n, const double* x, const double* l, const double* u, double lambda,
+                             unsigned flags, double* values, mir_least_squares_result_d* results, int device);
+int mir_fit_spline_batched_s(const mir_least_squares_settings_s* settings, size_t batch, size_t points, const float* points_x,
+                             const float* points_y, size_t n, const float* x, const float* l, const float* u, float lambda,
+                             unsigned flags, float* values, mir_least_squares_result_s* results, int device);
+
+/*
  * solveBoxQP (BQ:85-102, simple overload; BQ:122-379 full algorithm):
  *   argmin 1/2 x'Px + q'x  s.t.  l <= x <= u,   P n x n row-major, only the lower triangle read.
  * Single problem, host pointers; returns mir_box_qp_status, or -mir_b200_error on failure

@@ -46,11 +46,13 @@ class ModelId(enum.IntEnum):
     GAUSS4 = 6
     SUMEXP = 7
     GAUSSMIX = 8
+    SPLINE = 9
 
 
 MODEL_FD_JACOBIAN = 1
 MODEL_GRID_PER_PROBLEM = 2
 MODEL_NO_TAIL_SHORTCUT = 4
+MODEL_AUX_PER_PROBLEM = 8
 
 
 def _settings_types(real):
@@ -139,6 +141,7 @@ B200_SYMBOLS = [
     "mir_optimize_least_squares_sharded_d", "mir_b200_syrk_lower_dev_d",
     "mir_b200_posvx_batched_d", "mir_b200_posvx_batched_s",
     "mir_b200_nccl_unique_id", "mir_b200_nccl_comm_init", "mir_b200_nccl_comm_destroy",
+    "mir_fit_spline_d", "mir_fit_spline_s", "mir_fit_spline_batched_d", "mir_fit_spline_batched_s",
 ]
 
 
@@ -192,6 +195,11 @@ def bind_b200_abi(lib):
     for sfx in ("d", "s"):
         fn = getattr(lib, f"mir_b200_posvx_batched_{sfx}")
         fn.argtypes = [C.c_int, C.c_size_t, C.c_size_t, vp, vp, vp, vp, vp, C.c_int]; fn.restype = C.c_int
+    for sfx, S, R, real in (("d", LeastSquaresSettingsD, LeastSquaresResultD, C.c_double), ("s", LeastSquaresSettingsS, LeastSquaresResultS, C.c_float)):
+        fn = getattr(lib, f"mir_fit_spline_{sfx}")
+        fn.argtypes = [C.POINTER(S), C.c_size_t, vp, vp, C.c_size_t, vp, vp, vp, real, vp, C.POINTER(R)]; fn.restype = C.c_int
+        fn = getattr(lib, f"mir_fit_spline_batched_{sfx}")
+        fn.argtypes = [C.POINTER(S), C.c_size_t, C.c_size_t, vp, vp, C.c_size_t, vp, vp, vp, real, C.c_uint, vp, vp, C.c_int]; fn.restype = C.c_int
     lib.mir_b200_nccl_unique_id.argtypes = [vp]; lib.mir_b200_nccl_unique_id.restype = C.c_int
     lib.mir_b200_nccl_comm_init.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int]; lib.mir_b200_nccl_comm_init.restype = C.c_int
     lib.mir_b200_nccl_comm_destroy.argtypes = [vp]; lib.mir_b200_nccl_comm_destroy.restype = C.c_int

@@ -7,6 +7,12 @@
 #include "lm_small_launch.cuh"
 #include "runtime.cuh"
 
+namespace mirb200 {
+// general batched kernel, one CTA per problem, any n <= 128 (lm_cta.cuh / lm_cta_inst.cu)
+template <class T>
+int launch_cta_model(const mir_model_desc& model, size_t n, const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream);
+}
+
 extern char** environ;
 
 namespace mirb200 {
@@ -16,6 +22,17 @@ namespace mirb200 {
 bool model_needs_data(unsigned model)
 {
     return !(model == MIR_MODEL_LINEAR2 || model == MIR_MODEL_ROSENBROCK || model == MIR_MODEL_SQRTCIRCLE);
+}
+// Shapes the specialised kernels (lm_tpp / lm_mux / lm_small) instantiate; everything else goes to the general kernel.
+static bool specialised_shape(unsigned model, size_t n)
+{
+    switch (model) {
+    case MIR_MODEL_LINEAR2: case MIR_MODEL_ROSENBROCK: case MIR_MODEL_SQRTCIRCLE: case MIR_MODEL_EXPDECAY2: return n == 2;
+    case MIR_MODEL_EXPTAU3: case MIR_MODEL_EXPDECAY3: return n == 3;
+    case MIR_MODEL_GAUSS4: return n == 4;
+    case MIR_MODEL_SUMEXP: return n == 4 || n == 8;
+    default: return false;
+    }
 }
 static int check_model_data(const mir_model_desc* model, size_t batch, size_t m)
 {
@@ -49,7 +66,14 @@ static int batched_dev(const typename Num<T>::Settings* settings, const mir_mode
     a.t = model->t; a.y = model->y; a.x = x; a.l = l; a.u = u; a.results = results;
     a.counter = counter; a.ready = ready; a.spin_limit = spinLimit; a.stats = stats; a.batch = batch; a.m = (unsigned)m;
     a.bound_stride = (unsigned)bound_stride; a.flags = model->flags;
-    rc = launch_small_model<T>(model->model, n, *settings, a, stream);
+    static const bool forceGeneral = [] { const char* e = std::getenv("MIRB200_BATCH_KERNEL"); return e && !std::strcmp(e, "cta"); }();   // tests / experiments
+    if (specialised_shape(model->model, n) && !forceGeneral) {
+        rc = launch_small_model<T>(model->model, n, *settings, a, stream);
+        // a shape the specialised kernels do not cover after all (m beyond their rows-per-lane instantiations): general kernel
+        if (rc == MIR_B200_EUNSUPPORTED && model_needs_data(model->model)) { clear_error(); rc = launch_cta_model<T>(*model, n, *settings, a, stream); }
+    } else {
+        rc = launch_cta_model<T>(*model, n, *settings, a, stream);
+    }
     cudaFreeAsync(counter, stream);
     return rc;
 }
@@ -87,6 +111,7 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     const size_t xBytes = sizeof(T) * batch * n;
     const size_t bBytes = sizeof(T) * (bound_stride ? batch * bound_stride : n);
     const size_t rBytes = sizeof(Result) * batch;
+    const size_t aBytes = model->aux ? sizeof(T) * ((model->flags & MIR_MODEL_AUX_PER_PROBLEM) ? batch * n : n) : 0;
 
     // Pipeline ("staged").  ONE kernel launch for the whole batch (chunked launches lose ~15 % to queue drain at this grid
     // size) that runs BESIDE the copies feeding it: the per-problem inputs go to the device on a copy stream in chunks of
@@ -128,7 +153,7 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     *h_flag = 0;
 
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t total = align(tBytes) + align(yBytes) + align(xBytes) + 2 * align(bBytes) + align(rBytes) + align(sizeof(mir_batch_stats)) + 256;
+    const size_t total = align(tBytes) + align(yBytes) + align(xBytes) + 2 * align(bBytes) + align(rBytes) + align(sizeof(mir_batch_stats)) + align(aBytes) + 256;
     char* base = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&base, total, cs);
     if (e != cudaSuccess) { cleanup(); return check_cuda(e, "cudaMallocAsync(batch buffers)"); }
@@ -140,6 +165,7 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     T* du = (T*)p; p += align(bBytes);
     Result* dr = (Result*)p; p += align(rBytes);
     mir_batch_stats* ds = (mir_batch_stats*)p; p += align(sizeof(mir_batch_stats));
+    T* da = (T*)p; p += align(aBytes);
     unsigned int* d_ready = (unsigned int*)p;                     // {watermark, time-out flag}
 
     // shared inputs, counters and the watermark (0 = nothing staged) on the compute stream; the copy stream starts behind them
@@ -148,6 +174,7 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
         CK(cudaMemcpyAsync(dl, l, bBytes, cudaMemcpyHostToDevice, cs), "H2D l");
         CK(cudaMemcpyAsync(du, u, bBytes, cudaMemcpyHostToDevice, cs), "H2D u");
     }
+    if (aBytes) CK(cudaMemcpyAsync(da, model->aux, aBytes, cudaMemcpyHostToDevice, cs), "H2D aux");
     if (stats) CK(cudaMemsetAsync(ds, 0, sizeof(mir_batch_stats), cs), "memset stats");
     CK(cudaMemsetAsync(d_ready, 0, 2 * sizeof(unsigned int), cs), "memset watermark");
     CK(cudaEventRecord(ev, cs), "cudaEventRecord");
@@ -171,7 +198,7 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
     }
     auto launch = [&](const unsigned int* ready) {
         mir_model_desc dm = *model;
-        dm.t = tBytes ? dt : nullptr; dm.y = yBytes ? dy : nullptr;
+        dm.t = tBytes ? dt : nullptr; dm.y = yBytes ? dy : nullptr; dm.aux = aBytes ? da : nullptr;
         if (rc == MIR_B200_OK) rc = batched_dev<T>(settings, &dm, batch, m, n, dx, dl, du, bound_stride, dr, stats ? ds : nullptr, cs, ready, spinLimit);
     };
     if (staged) {

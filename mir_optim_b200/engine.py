@@ -57,7 +57,7 @@ class Engine(ReferenceAPI):
     def optimize_batched(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
                          t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
                          fd_jacobian: bool = False, want_stats: bool = False, device: int = -1, tail_shortcut: bool = True,
-                         results: np.ndarray | None = None):
+                         results: np.ndarray | None = None, aux: np.ndarray | None = None, param: float = 0.0):
         """Solve ``batch`` independent problems; x (batch, n) is updated in place.
         l/u: shape (n,) shared, or (batch, n).  Returns (results structured array, stats dict | None).
         results: optional preallocated structured array (e.g. a view of pinned memory) to receive the Result PODs."""
@@ -76,7 +76,11 @@ class Engine(ReferenceAPI):
             if t.ndim == 2:
                 flags |= MODEL_GRID_PER_PROBLEM
         assert m is not None, "m is required for data-free models"
-        desc = ModelDesc(int(model), flags, _vp(t), _vp(y))
+        if aux is not None:
+            aux = np.ascontiguousarray(aux, dtype=x.dtype)
+            if aux.ndim == 2:
+                flags |= _abi.MODEL_AUX_PER_PROBLEM
+        desc = ModelDesc(int(model), flags, _vp(t), _vp(y), _vp(aux), float(param))
         if results is None:
             results = np.empty(batch, dtype=RESULT_DTYPES[x.dtype])
         assert results.dtype == RESULT_DTYPES[x.dtype] and results.shape == (batch,) and results.flags.c_contiguous
@@ -113,6 +117,37 @@ class Engine(ReferenceAPI):
                 _vp(results), _vp(stats), C.c_void_p(stream))
         self._check(rc)
         return results
+
+    # -- fitSpline (fit_splie.d:26-85) ------------------------------------------------------
+    def fit_spline(self, settings, points: np.ndarray, x: np.ndarray, l: np.ndarray, u: np.ndarray, lam: float = 0.0):
+        """The reference's ``fitSpline(settings, points, x, l, u, lambda)``: points (P, 2) = [x_i, y_i], x = knots.
+        Returns (values at the knots, LeastSquaresResult); raises ValueError with the reference's message where it throws
+        (points.length < x.length with lambda == 0, fit_splie.d:45-49)."""
+        points = np.ascontiguousarray(points)
+        v, r = self.fit_spline_batched(settings, points[:, 0], points[None, :, 1], x, l, u, lam)
+        return v[0], r[0]
+
+    def fit_spline_batched(self, settings, points_x: np.ndarray, points_y: np.ndarray, x: np.ndarray, l: np.ndarray, u: np.ndarray,
+                           lam: float = 0.0, device: int = -1, tail_shortcut: bool = True):
+        """Many curves at once: points_y (batch, P); points_x (P,) shared or (batch, P); knots x (n,) shared or (batch, n);
+        bounds l / u (n,).  Returns (values (batch, n), results structured array)."""
+        dt = np.dtype(points_y.dtype)
+        sfx, real, S, R, *_ = _types(dt)
+        assert isinstance(settings, S)
+        points_y = np.ascontiguousarray(points_y); batch, P = points_y.shape
+        points_x = np.ascontiguousarray(points_x, dtype=dt); x = np.ascontiguousarray(x, dtype=dt)
+        l = np.ascontiguousarray(l, dtype=dt); u = np.ascontiguousarray(u, dtype=dt)
+        n = x.shape[-1]
+        flags = (MODEL_GRID_PER_PROBLEM if points_x.ndim == 2 else 0) | (_abi.MODEL_AUX_PER_PROBLEM if x.ndim == 2 else 0)
+        flags |= 0 if tail_shortcut else MODEL_NO_TAIL_SHORTCUT
+        values = np.empty((batch, n), dtype=dt)
+        results = np.empty(batch, dtype=RESULT_DTYPES[dt])
+        rc = getattr(self.lib, f"mir_fit_spline_batched_{sfx}")(C.byref(settings), batch, P, _vp(points_x), _vp(points_y), n, _vp(x), _vp(l), _vp(u),
+                                                                 real(lam), flags, _vp(values), _vp(results), device)
+        if rc == 2 and b"fitSpline:" in self.lib.mir_b200_last_error():
+            raise ValueError(self.lib.mir_b200_last_error().decode())
+        self._check(rc)
+        return values, results
 
     # -- solveBoxQP (boxcqp.d:85-102) -----------------------------------------------------
     def solve_box_qp(self, P: np.ndarray, q: np.ndarray, l: np.ndarray, u: np.ndarray, x: np.ndarray, settings=None):

@@ -13,7 +13,7 @@ def _vp(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
-def oracle_batched(lib, settings, model, x0, l, u, t=None, y=None, m=None, fd_jacobian=False, nthreads=0):
+def oracle_batched(lib, settings, model, x0, l, u, t=None, y=None, m=None, fd_jacobian=False, nthreads=0, aux=None, param=0.0):
     """Runs the oracle LM (least_squares.d:877-1176 restated) on every problem.  Returns (x, results, threads)."""
     x = np.array(x0, copy=True, order="C")
     dt = x.dtype
@@ -29,7 +29,11 @@ def oracle_batched(lib, settings, model, x0, l, u, t=None, y=None, m=None, fd_ja
         t = np.ascontiguousarray(t, dtype=dt)
         if t.ndim == 2:
             flags |= MODEL_GRID_PER_PROBLEM
-    desc = ModelDesc(int(model), flags, _vp(t), _vp(y))
+    if aux is not None:
+        aux = np.ascontiguousarray(aux, dtype=dt)
+        if aux.ndim == 2:
+            flags |= 8                         # MIR_MODEL_AUX_PER_PROBLEM
+    desc = ModelDesc(int(model), flags, _vp(t), _vp(y), _vp(aux), float(param))
     results = np.empty(batch, dtype=RESULT_DTYPES[dt])
     fn = getattr(lib, f"oracle_batched_{sfx}")
     fn.restype = C.c_int
