@@ -18,8 +18,12 @@
 #ifndef MIR_OPTIM_B200_H
 #define MIR_OPTIM_B200_H
 
+#ifdef __CUDACC_RTC__   /* run-time compilation of user models (NVRTC has no C library headers) */
+typedef unsigned long long uint64_t; typedef unsigned int uint32_t; typedef int int32_t; typedef unsigned long uintptr_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -237,7 +241,8 @@ typedef enum mir_model_id {
     MIR_MODEL_SPLINE        = 9,  /* fitSpline's residual (fit_splie.d:58-80): p = values of a C2 cubic spline
                                      (not-a-knot ends) at the knots `aux`; r_i = spline(t_i) - y_i, last row =
                                      sqrt(param * integral term); n = number of knots >= 2; finite differences only */
-    MIR_MODEL_COUNT_
+    MIR_MODEL_COUNT_,
+    MIR_MODEL_USER_BASE     = 0x1000  /* ids returned by mir_b200_model_compile (models compiled at run time) */
 } mir_model_id;
 
 enum {
@@ -256,6 +261,29 @@ typedef struct mir_model_desc {
     const void* aux;     /* model constants, T[n] (shared) or T[batch*n]: the knots of MIR_MODEL_SPLINE; else NULL */
     double      param;   /* model constant: the smoothing weight lambda of MIR_MODEL_SPLINE; else 0  */
 } mir_model_desc;
+
+/*
+ * User-defined residual models on the device (the reference takes arbitrary f / g, LS:78-80).  `source`
+ * is CUDA C++ defining, in the global namespace,
+ *
+ *     template <class REAL> struct UserModel {
+ *         static constexpr bool kAnalytic = false;       // true: jacobian() below is provided
+ *         // residual of row `row` (0 <= row < m) for the parameters p[n]; t, y: the row's entries of model->t / model->y
+ *         // (0 when those are NULL); aux: model->aux of this problem (may be NULL); param: model->param
+ *         __device__ static REAL residual(const REAL* p, int n, int m, int row, REAL t, REAL y, const REAL* aux, REAL param);
+ *         // row `row` of the Jacobian, d residual / d p[k] into Jrow[k]
+ *         __device__ static void jacobian(const REAL* p, int n, int m, int row, REAL t, REAL y, const REAL* aux, REAL param, REAL* Jrow);
+ *     };
+ *
+ * It is compiled with NVRTC for sm_100a together with the general batched LM kernel (lm_cta.cuh, whose sources are
+ * embedded in the library) at the first use per precision; the returned id (>= MIR_MODEL_USER_BASE) goes into
+ * mir_model_desc.model of the batched entry points -- or of the legacy entry point in device-model mode, which gives the
+ * reference's own signature a GPU path for user models.  libnvrtc.so.12 and libcuda.so.1 are bound at run time.
+ * Compile errors: MIR_B200_EINVAL, the NVRTC log is in mir_b200_last_error().  Without this, arbitrary f / g passed as
+ * host function pointers run on the host with one transfer of y (and J) per pass (host-callback mode).
+ */
+int  mir_b200_model_compile(const char* source, uint32_t* model_id);
+int  mir_b200_model_release(uint32_t model_id);
 
 /* Sentinels for the legacy entry points: pass as `f` / `g` with fContext = mir_model_desc*. */
 void mir_b200_device_model_d    (void* context, size_t m, size_t n, const double* x, double* y);

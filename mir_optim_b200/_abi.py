@@ -142,6 +142,7 @@ B200_SYMBOLS = [
     "mir_b200_posvx_batched_d", "mir_b200_posvx_batched_s",
     "mir_b200_nccl_unique_id", "mir_b200_nccl_comm_init", "mir_b200_nccl_comm_destroy",
     "mir_fit_spline_d", "mir_fit_spline_s", "mir_fit_spline_batched_d", "mir_fit_spline_batched_s",
+    "mir_b200_model_compile", "mir_b200_model_release",
 ]
 
 
@@ -200,6 +201,8 @@ def bind_b200_abi(lib):
         fn.argtypes = [C.POINTER(S), C.c_size_t, vp, vp, C.c_size_t, vp, vp, vp, real, vp, C.POINTER(R)]; fn.restype = C.c_int
         fn = getattr(lib, f"mir_fit_spline_batched_{sfx}")
         fn.argtypes = [C.POINTER(S), C.c_size_t, C.c_size_t, vp, vp, C.c_size_t, vp, vp, vp, real, C.c_uint, vp, vp, C.c_int]; fn.restype = C.c_int
+    lib.mir_b200_model_compile.argtypes = [C.c_char_p, C.POINTER(C.c_uint32)]; lib.mir_b200_model_compile.restype = C.c_int
+    lib.mir_b200_model_release.argtypes = [C.c_uint32]; lib.mir_b200_model_release.restype = C.c_int
     lib.mir_b200_nccl_unique_id.argtypes = [vp]; lib.mir_b200_nccl_unique_id.restype = C.c_int
     lib.mir_b200_nccl_comm_init.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int]; lib.mir_b200_nccl_comm_init.restype = C.c_int
     lib.mir_b200_nccl_comm_destroy.argtypes = [vp]; lib.mir_b200_nccl_comm_destroy.restype = C.c_int

@@ -12,7 +12,6 @@
 //                 Active-set sub-systems are compacted through the ascending free-index list,
 //                 exactly like boxcqp.d:269-305.
 #pragma once
-#include <type_traits>
 #include "boxqp_small.cuh"   // KBN
 #include "common.cuh"
 

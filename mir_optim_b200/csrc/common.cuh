@@ -1,8 +1,10 @@
 // common.cuh -- shared device/host plumbing for the B200 LM engine (sm_100a only).
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/mir_optim_b200.h"
 
@@ -21,7 +23,11 @@ template <> struct Num<double> {
     using Settings = mir_least_squares_settings_d;
     using Result = mir_least_squares_result_d;
     using QPSettings = mir_box_qp_settings_d;
+#ifdef __CUDACC_RTC__
+    __device__ static double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+#else
     __host__ __device__ static constexpr double inf() { return __builtin_huge_val(); }
+#endif
     __host__ __device__ static constexpr double lapack_eps() { return 0x1p-53; }      // dlamch('Epsilon')
     __host__ __device__ static constexpr double safmin() { return 0x1p-1022; }         // dlamch('Safe minimum')
     __host__ __device__ static constexpr double small_() { return 0x1p-970; }          // safmin / dlamch('Precision')
@@ -33,7 +39,11 @@ template <> struct Num<float> {
     using Settings = mir_least_squares_settings_s;
     using Result = mir_least_squares_result_s;
     using QPSettings = mir_box_qp_settings_s;
+#ifdef __CUDACC_RTC__
+    __device__ static float inf() { return __int_as_float(0x7f800000); }
+#else
     __host__ __device__ static constexpr float inf() { return __builtin_huge_valf(); }
+#endif
     __host__ __device__ static constexpr float lapack_eps() { return 0x1p-24f; }
     __host__ __device__ static constexpr float safmin() { return 0x1p-126f; }
     __host__ __device__ static constexpr float small_() { return 0x1p-103f; }

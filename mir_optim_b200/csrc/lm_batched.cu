@@ -21,7 +21,7 @@ namespace mirb200 {
 // caller's contract, stated in the header); only LINEAR2, ROSENBROCK and SQRTCIRCLE are data-free.
 bool model_needs_data(unsigned model)
 {
-    return !(model == MIR_MODEL_LINEAR2 || model == MIR_MODEL_ROSENBROCK || model == MIR_MODEL_SQRTCIRCLE);
+    return !(model == MIR_MODEL_LINEAR2 || model == MIR_MODEL_ROSENBROCK || model == MIR_MODEL_SQRTCIRCLE || model >= (unsigned)MIR_MODEL_USER_BASE);
 }
 // Shapes the specialised kernels (lm_tpp / lm_mux / lm_small) instantiate; everything else goes to the general kernel.
 static bool specialised_shape(unsigned model, size_t n)
@@ -70,7 +70,7 @@ static int batched_dev(const typename Num<T>::Settings* settings, const mir_mode
     if (specialised_shape(model->model, n) && !forceGeneral) {
         rc = launch_small_model<T>(model->model, n, *settings, a, stream);
         // a shape the specialised kernels do not cover after all (m beyond their rows-per-lane instantiations): general kernel
-        if (rc == MIR_B200_EUNSUPPORTED && model_needs_data(model->model)) { clear_error(); rc = launch_cta_model<T>(*model, n, *settings, a, stream); }
+        if (rc == MIR_B200_EUNSUPPORTED && model_needs_data(model->model) && batch > 1) { clear_error(); rc = launch_cta_model<T>(*model, n, *settings, a, stream); }
     } else {
         rc = launch_cta_model<T>(*model, n, *settings, a, stream);
     }

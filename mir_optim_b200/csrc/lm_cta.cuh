@@ -26,7 +26,9 @@
 #include "boxqp_cta.cuh"
 #include "lm_small.cuh"
 #include "models_large.cuh"
+#ifndef __CUDACC_RTC__
 #include "runtime.cuh"
+#endif
 
 namespace mirb200 {
 
@@ -190,11 +192,28 @@ template <class T> struct CtaSpline {
     __device__ static void jacobian_row(const CtaProblem<T>&, const T*, const T*, int, T*) {}
 };
 
+// ---- a model compiled at run time (mir_b200_model_compile, lm_nvrtc.cu): the user's UserModel<REAL> behind the interface
+template <class U, class T> struct CtaUser {
+    static constexpr bool kAnalytic = U::kAnalytic;
+    __host__ __device__ static bool valid(int, int) { return true; }
+    __host__ __device__ static int prep_elems(int) { return 1; }
+    __device__ static void prepare(const CtaProblem<T>&, const T*, T*) { __syncthreads(); }
+    __device__ static T residual(const CtaProblem<T>& pb, const T* p, const T*, int row)
+    {
+        return U::residual(p, pb.n, pb.m, row, pb.t ? pb.t[row] : (T)0, pb.y ? pb.y[row] : (T)0, pb.aux, pb.param);
+    }
+    __device__ static void jacobian_row(const CtaProblem<T>& pb, const T* p, const T*, int row, T* Jrow)
+    {
+        if constexpr (U::kAnalytic) U::jacobian(p, pb.n, pb.m, row, pb.t ? pb.t[row] : (T)0, pb.y ? pb.y[row] : (T)0, pb.aux, pb.param, Jrow);
+    }
+};
+
 template <class Model, class T, bool FD>
 __global__ void __launch_bounds__(CTA_NT)
 lm_cta_kernel(const typename Num<T>::Settings st, const CtaBatchArgs ca)
 {
     constexpr int NT = CTA_NT;
+    constexpr bool useFD = FD || !Model::kAnalytic;       // no analytic Jacobian: g == null semantics whatever was asked for
     using Result = typename Num<T>::Result;
     const SmallBatchArgs& args = ca.b;
     const int tid = threadIdx.x;
@@ -289,7 +308,7 @@ lm_cta_kernel(const typename Num<T>::Settings st, const CtaBatchArgs ca)
             return cta_sum_all(part, red4);
         };
 
-        const unsigned maxAge = st.maxAge ? st.maxAge : (FD ? 2u * (unsigned)n : 3u);               // LS:945
+        const unsigned maxAge = st.maxAge ? st.maxAge : (useFD ? 2u * (unsigned)n : 3u);               // LS:945
         T* y = vec0; T* mb = vec1;
         ret.fCalls = 1;
         ret.residual = eval(x, y);                                                                  // LS:953-955
@@ -345,7 +364,7 @@ lm_cta_kernel(const typename Num<T>::Settings st, const CtaBatchArgs ca)
                     }
                 } else {
                     age = 0; ++sFresh;                                                              // LS:1010
-                    if (!FD && Model::kAnalytic) {                                                  // LS:1011-1015
+                    if constexpr (!useFD) {                                                         // LS:1011-1015
                         ++ret.gCalls;
                         Model::prepare(pb, x, prepA);
                         for (int r = tid; r < m; r += NT) Model::jacobian_row(pb, x, prepA, r, J + (size_t)r * n);
@@ -507,6 +526,7 @@ lm_cta_kernel(const typename Num<T>::Settings st, const CtaBatchArgs ca)
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
+#ifndef __CUDACC_RTC__
 template <class T> size_t cta_smem_bytes(int n, int prepElems)
 {
     return sizeof(T) * ((size_t)10 * n + 8 + prepElems + 1) + CtaQPScratch<T>::bytes(n) + 16;
@@ -549,5 +569,9 @@ int launch_cta(const typename Num<T>::Settings& st, const SmallBatchArgs& args, 
 // general batched path by model id; MIR_B200_EUNSUPPORTED if the model has no run-time-n functor
 template <class T>
 int launch_cta_model(const mir_model_desc& model, size_t n, const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream);
+// models compiled at run time (lm_nvrtc.cu)
+template <class T>
+int launch_user_model(const mir_model_desc& model, size_t n, const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream);
+#endif  // !__CUDACC_RTC__
 
 }  // namespace mirb200

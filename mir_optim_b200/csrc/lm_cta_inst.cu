@@ -7,6 +7,7 @@ namespace mirb200 {
 template <class T>
 int launch_cta_model(const mir_model_desc& model, size_t n, const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
+    if (model.model >= (uint32_t)MIR_MODEL_USER_BASE) return launch_user_model<T>(model, n, st, args, stream);
     switch (model.model) {
     case MIR_MODEL_EXPDECAY2: return launch_cta<CtaFromLarge<LModelExpDecay2<T>, T>, T>(st, args, n, model, stream);
     case MIR_MODEL_EXPTAU3:   return launch_cta<CtaFromLarge<LModelExpTau3<T>, T>, T>(st, args, n, model, stream);

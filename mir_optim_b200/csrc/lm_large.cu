@@ -450,10 +450,17 @@ static typename Num<T>::Result legacy_entry(const typename Num<T>::Settings* set
         if (g && (void*)g != Sentinels<T>::g()) { set_error("mir_optim_b200: device-model mode takes g = NULL (finite differences) or mir_b200_device_model_jac_*"); return ret; }
         mir_model_desc d = *desc;
         d.flags = (d.flags & (uint32_t)MIR_MODEL_NO_TAIL_SHORTCUT) | (g ? 0u : (uint32_t)MIR_MODEL_FD_JACOBIAN);
-        // small shapes: the register-resident kernel (one warp for the whole problem)
-        int rc = batched_host_entry<T>(settings, &d, 1, m, n, x, l, u, 0, &ret, nullptr, -1);
-        if (rc == MIR_B200_OK) return ret;
-        if (rc != MIR_B200_EUNSUPPORTED) { ret.status = mir_ls_numericError; return ret; }
+        // small shapes, fitSpline's residual and models compiled at run time: the batched kernels with a batch of one;
+        // many rows of a model the row-parallel engine knows: that engine
+        const bool rowEngineModel = d.model == MIR_MODEL_EXPDECAY2 || d.model == MIR_MODEL_EXPTAU3 || d.model == MIR_MODEL_EXPDECAY3 ||
+                                    d.model == MIR_MODEL_GAUSS4 || d.model == MIR_MODEL_SUMEXP || d.model == MIR_MODEL_GAUSSMIX;
+        int rc = MIR_B200_EUNSUPPORTED;
+        if (!(rowEngineModel && m > 128)) {
+            d.aux = desc->aux; d.param = desc->param;
+            rc = batched_host_entry<T>(settings, &d, 1, m, n, x, l, u, 0, &ret, nullptr, -1);
+            if (rc == MIR_B200_OK) return ret;
+            if (rc != MIR_B200_EUNSUPPORTED || !rowEngineModel) { ret.status = mir_ls_numericError; return ret; }
+        }
         clear_error();
         if (require_device(-1)) return ret;
         cudaStream_t stream = nullptr;

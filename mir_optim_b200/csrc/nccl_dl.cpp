@@ -39,7 +39,7 @@ Api& api()
     std::call_once(once, [] {
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* nm : names) { a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (a.handle) break; }
-        if (!a.handle) { a.why = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?"); return; }
+        if (!a.handle) { const char* e = dlerror(); a.why = std::string("dlopen(libnccl.so.2) failed: ") + (e ? e : "?"); return; }
         a.getUniqueId = (GetUniqueId_t)dlsym(a.handle, "ncclGetUniqueId");
         a.commInitRank = (CommInitRank_t)dlsym(a.handle, "ncclCommInitRank");
         a.commDestroy = (CommDestroy_t)dlsym(a.handle, "ncclCommDestroy");

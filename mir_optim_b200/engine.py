@@ -118,6 +118,18 @@ class Engine(ReferenceAPI):
         self._check(rc)
         return results
 
+    # -- user-defined device models (NVRTC) ---------------------------------------------------
+    def compile_model(self, cuda_source: str) -> int:
+        """Registers a residual model written in CUDA C++ (``template <class REAL> struct UserModel {...}``, see
+        include/mir_optim_b200.h) and returns its model id, usable wherever a ModelId is.  Raises B200Error with the NVRTC
+        log if the source does not compile."""
+        mid = C.c_uint32()
+        self._check(self.lib.mir_b200_model_compile(cuda_source.encode(), C.byref(mid)))
+        return int(mid.value)
+
+    def release_model(self, model_id: int):
+        self._check(self.lib.mir_b200_model_release(int(model_id)))
+
     # -- fitSpline (fit_splie.d:26-85) ------------------------------------------------------
     def fit_spline(self, settings, points: np.ndarray, x: np.ndarray, l: np.ndarray, u: np.ndarray, lam: float = 0.0):
         """The reference's ``fitSpline(settings, points, x, l, u, lambda)``: points (P, 2) = [x_i, y_i], x = knots.
@@ -201,7 +213,7 @@ class Engine(ReferenceAPI):
     # -- one problem through the reference's own entry point, residual model on the device ------
     def optimize_device_model(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
                               t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
-                              fd_jacobian: bool = False, tail_shortcut: bool = True):
+                              fd_jacobian: bool = False, tail_shortcut: bool = True, aux: np.ndarray | None = None, param: float = 0.0):
         """mir_optimize_least_squares_{d,s} (least_squares.d:705-748) with f = mir_b200_device_model_*:
         the whole solve, residuals included, runs on the GPU.  x (n,) in/out.  Returns the Result POD."""
         sfx, real, S, R, Sl, FT, _ = _types(x.dtype)
@@ -212,7 +224,9 @@ class Engine(ReferenceAPI):
         if t is not None:
             t = np.ascontiguousarray(t, dtype=x.dtype).reshape(-1)
         l = np.ascontiguousarray(l, dtype=x.dtype); u = np.ascontiguousarray(u, dtype=x.dtype)
-        desc = ModelDesc(int(model), 0 if tail_shortcut else MODEL_NO_TAIL_SHORTCUT, _vp(t), _vp(y))
+        if aux is not None:
+            aux = np.ascontiguousarray(aux, dtype=x.dtype).reshape(-1)
+        desc = ModelDesc(int(model), 0 if tail_shortcut else MODEL_NO_TAIL_SHORTCUT, _vp(t), _vp(y), _vp(aux), float(param))
         f_ptr = C.cast(getattr(self.lib, f"mir_b200_device_model_{sfx}"), C.c_void_p)
         g_ptr = None if fd_jacobian else C.cast(getattr(self.lib, f"mir_b200_device_model_jac_{sfx}"), C.c_void_p)
         fn = getattr(self.lib, f"mir_optimize_least_squares_{sfx}")
