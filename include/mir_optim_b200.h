@@ -250,7 +250,11 @@ enum {
     MIR_MODEL_GRID_PER_PROBLEM = 2u,  /* t has batch*m entries instead of m shared ones              */
     MIR_MODEL_NO_TAIL_SHORTCUT = 4u,  /* verification only: execute every pass of the lambda-overflow tail
                                          instead of fast-forwarding it (results are identical) */
-    MIR_MODEL_AUX_PER_PROBLEM  = 8u   /* aux has batch*n entries instead of n shared ones                   */
+    MIR_MODEL_AUX_PER_PROBLEM  = 8u,  /* aux has batch*n entries instead of n shared ones                   */
+    MIR_MODEL_WARM_START       = 16u  /* batched entries: results[b].lambda on entry (> 0, finite) is the initial
+                                         damping instead of 0 (LS:966); the reference documents Result.lambda as
+                                         the initial trust-region value (LS:141-142) but never reads it back.
+                                         Chain it with the x of a previous call to continue a fit.            */
 };
 
 typedef struct mir_model_desc {

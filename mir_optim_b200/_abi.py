@@ -53,6 +53,7 @@ MODEL_FD_JACOBIAN = 1
 MODEL_GRID_PER_PROBLEM = 2
 MODEL_NO_TAIL_SHORTCUT = 4
 MODEL_AUX_PER_PROBLEM = 8
+MODEL_WARM_START = 16
 
 
 def _settings_types(real):

@@ -186,6 +186,7 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
         if (tBytes && per) CK(cudaMemcpyAsync(dt + lo * m, static_cast<const T*>(model->t) + lo * m, sizeof(T) * nb * m, cudaMemcpyHostToDevice, ps), "H2D t");
         if (yBytes) CK(cudaMemcpyAsync(dy + lo * m, static_cast<const T*>(model->y) + lo * m, sizeof(T) * nb * m, cudaMemcpyHostToDevice, ps), "H2D y");
         CK(cudaMemcpyAsync(dx + lo * n, x + lo * n, sizeof(T) * nb * n, cudaMemcpyHostToDevice, ps), "H2D x");
+        if (model->flags & MIR_MODEL_WARM_START) CK(cudaMemcpyAsync(dr + lo, results + lo, sizeof(Result) * nb, cudaMemcpyHostToDevice, ps), "H2D results (warm start)");
         if (bound_stride) {
             CK(cudaMemcpyAsync(dl + lo * bound_stride, l + lo * bound_stride, sizeof(T) * nb * bound_stride, cudaMemcpyHostToDevice, ps), "H2D l");
             CK(cudaMemcpyAsync(du + lo * bound_stride, u + lo * bound_stride, sizeof(T) * nb * bound_stride, cudaMemcpyHostToDevice, ps), "H2D u");
@@ -227,6 +228,7 @@ static int batched_host(const typename Num<T>::Settings* settings, const mir_mod
             // the kernel gave up waiting for its inputs (the copies could not run beside it): every input is resident
             // now, x was partly overwritten by the problems that did run -- restore it and run the batch plainly
             CK(cudaMemcpyAsync(dx, x, xBytes, cudaMemcpyHostToDevice, cs), "H2D x (re-run)");
+            if (model->flags & MIR_MODEL_WARM_START) CK(cudaMemcpyAsync(dr, results, rBytes, cudaMemcpyHostToDevice, cs), "H2D results (re-run)");
             if (stats) CK(cudaMemsetAsync(ds, 0, sizeof(mir_batch_stats), cs), "memset stats");
             launch(nullptr);
         }

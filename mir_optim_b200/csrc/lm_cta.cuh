@@ -315,7 +315,7 @@ lm_cta_kernel(const typename Num<T>::Settings st, const CtaBatchArgs ca)
         bool fConverged = ret.residual <= st.maxGoodResidual;                                       // LS:956
         bool needJacobian = true;
         unsigned age = maxAge;
-        T lambda = (T)0, mu = (T)1, deltaX_dot = (T)0;
+        T lambda = warm_lambda<T>(args, prob), mu = (T)1, deltaX_dot = (T)0;
         ret.status = mir_ls_maxIterations;                                                          // LS:959-971
         bool jjValid = false;
 

@@ -589,7 +589,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                                 xt = x; dX = (T)0; Jy = (T)0; ysel = 0;
                                 maxAge = st.maxAge ? st.maxAge : (FD ? 2u * N : 3u);                                 // LS:945
                                 iterations = 0; fCalls = 0; gCalls = 0; status = mir_ls_maxIterations;               // LS:959-971
-                                residual = Num<T>::inf(); lambda = (T)0; mu = (T)1; deltaX_dot = (T)0;
+                                residual = Num<T>::inf(); lambda = warm_lambda<T>(args, prob); mu = (T)1; deltaX_dot = (T)0;
                                 age = maxAge; needJacobian = false; fConverged = false; jacMode = 0;
                                 rf = MUX_EVAL_INIT;                                                                  // initial residual, LS:953-956
                             }

@@ -68,6 +68,17 @@ __device__ __forceinline__ bool wait_staged(const unsigned int* ready, unsigned 
     }
 }
 
+
+// Warm start (MIR_MODEL_WARM_START; the reference documents Result.lambda as the "(inverse of) initial trust region
+// radius", LS:141-142, but always restarts from 0, LS:966 -- SURVEY 8f-4): the caller's Result.lambda, if it is a usable
+// damping value, replaces the 0.  A value >= minLambda also skips the 0.001 max diag(J^T J) initialisation, LS:1067-1072.
+template <class T> __device__ __forceinline__ T warm_lambda(const SmallBatchArgs& args, unsigned long long prob)
+{
+    if (!(args.flags & MIR_MODEL_WARM_START)) return (T)0;
+    const T v = static_cast<const typename Num<T>::Result*>(args.results)[prob].lambda;
+    return (v > (T)0 && v < Num<T>::inf()) ? v : (T)0;
+}
+
 #ifndef MIRB200_MINBLOCKS
 #define MIRB200_MINBLOCKS 1
 #endif
@@ -288,7 +299,7 @@ lm_small_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
             bool fConverged = ret.residual <= st.maxGoodResidual;                            // LS:956
             bool needJacobian = true;                                                        // LS:959-971
             unsigned age = maxAge;
-            T lambda = (T)0, mu = (T)1, deltaX_dot = (T)0;
+            T lambda = warm_lambda<T>(args, prob), mu = (T)1, deltaX_dot = (T)0;
             int status = mir_ls_maxIterations;
             unsigned iterations = 0;
 

@@ -57,7 +57,8 @@ class Engine(ReferenceAPI):
     def optimize_batched(self, settings, model: ModelId, x: np.ndarray, l: np.ndarray, u: np.ndarray,
                          t: np.ndarray | None = None, y: np.ndarray | None = None, m: int | None = None,
                          fd_jacobian: bool = False, want_stats: bool = False, device: int = -1, tail_shortcut: bool = True,
-                         results: np.ndarray | None = None, aux: np.ndarray | None = None, param: float = 0.0):
+                         results: np.ndarray | None = None, aux: np.ndarray | None = None, param: float = 0.0,
+                         warm_start: bool = False):
         """Solve ``batch`` independent problems; x (batch, n) is updated in place.
         l/u: shape (n,) shared, or (batch, n).  Returns (results structured array, stats dict | None).
         results: optional preallocated structured array (e.g. a view of pinned memory) to receive the Result PODs."""
@@ -80,6 +81,9 @@ class Engine(ReferenceAPI):
             aux = np.ascontiguousarray(aux, dtype=x.dtype)
             if aux.ndim == 2:
                 flags |= _abi.MODEL_AUX_PER_PROBLEM
+        if warm_start:
+            assert results is not None, "warm_start reads results['lambda'] of a previous call"
+            flags |= _abi.MODEL_WARM_START
         desc = ModelDesc(int(model), flags, _vp(t), _vp(y), _vp(aux), float(param))
         if results is None:
             results = np.empty(batch, dtype=RESULT_DTYPES[x.dtype])
