@@ -1,7 +1,12 @@
-// boxqp_batched.cu -- batched BOXCQP (BASELINE configs[4]a): one CTA per QP, persistent CTAs pulling QP
-// indices from an atomic counter; P's lower triangle, the factor and all vectors live in shared memory.
+// boxqp_batched.cu -- batched BOXCQP (BASELINE configs[4]a).  n <= 64: one WARP per QP (boxqp_warp.cuh: no barriers, packed
+// factor in shared memory, P read in place); 64 < n <= 128: one CTA per QP, P's lower triangle, the factor and all vectors in
+// shared memory.  Persistent warps / CTAs pull QP indices from an atomic counter.
 // C ABI: mir_solve_box_qp_{d,s}, mir_solve_box_qp_batched[_dev]_{d,s}  (solveBoxQP, boxcqp.d:85-102 / 122-379).
+#include <cstdlib>
+#include <cstring>
+
 #include "boxqp_cta.cuh"
+#include "boxqp_warp.cuh"
 #include "runtime.cuh"
 
 namespace mirb200 {
@@ -60,6 +65,33 @@ __global__ void __launch_bounds__(NT) boxqp_cta_kernel(const QPBatchArgs<T> a)
     }
 }
 
+// One warp (= one CTA) per QP, n <= 64.
+template <class T>
+__global__ void __launch_bounds__(32) boxqp_warp_kernel(const QPBatchArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpQPSmem<T>& sm = *reinterpret_cast<WarpQPSmem<T>*>(smem_raw);
+    const int n = a.n, lane = threadIdx.x;
+    for (;;) {
+        unsigned int prob = 0;
+        if (lane == 0) prob = atomicAdd(a.counter, 1u);
+        prob = __shfl_sync(0xffffffffu, prob, 0);
+        if (prob >= a.batch) break;
+        const T* Pg = a.P + (size_t)prob * n * n;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            sm.q[i] = a.q[(size_t)prob * n + i]; sm.l[i] = a.l[(size_t)prob * n + i]; sm.u[i] = a.u[(size_t)prob * n + i];
+            sm.x[i] = (T)0;
+        }
+        __syncwarp();
+        unsigned iters = 0, solves = 0;
+        const int st = boxqp_warp<T>(a.st, n, Pg, sm, lane, iters, solves);
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) a.x[(size_t)prob * n + i] = sm.x[i];
+        if (lane == 0) { a.status[prob] = st; if (a.iterations) a.iterations[prob] = iters; }
+    }
+}
+
 template <class T> static size_t qp_smem_bytes(int n, bool a_smem)
 {
     size_t b = ((CtaQPScratch<T>::bytes(n) + 15) & ~(size_t)15) + sizeof(T) * 4 * (size_t)n;
@@ -89,6 +121,23 @@ static int qp_batched_dev(const typename Num<T>::QPSettings* settings, size_t ba
     MIRB200_CUDA(cudaMallocAsync((void**)&a.counter, sizeof(unsigned int), stream));
     MIRB200_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream));
 
+    static const bool ctaOnly = [] { const char* e = std::getenv("MIRB200_QP_KERNEL"); return e && !std::strcmp(e, "cta"); }();   // experiments / tests
+    if (n <= (size_t)WQP_NMAX && !ctaOnly) {
+        auto wk = boxqp_warp_kernel<T>;
+        const size_t wsmem = sizeof(WarpQPSmem<T>);
+        MIRB200_CUDA(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        MIRB200_CUDA(cudaFuncSetAttribute(wk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int perSM = 0;
+        MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wk, 32, wsmem));
+        if (perSM < 1) perSM = 1;
+        size_t grid = (size_t)sm_count() * perSM;
+        if (batch < grid) grid = batch;
+        wk<<<(unsigned)grid, 32, wsmem, stream>>>(a);
+        count_launch();
+        rc = check_cuda(cudaGetLastError(), "boxqp_warp_kernel launch");
+        cudaFreeAsync(a.counter, stream);
+        return rc;
+    }
     const bool a_smem = qp_smem_bytes<T>((int)n, true) <= 100 * 1024;       // >= 2 CTAs per SM
     const size_t smem = qp_smem_bytes<T>((int)n, a_smem);
     auto kern = a_smem ? boxqp_cta_kernel<T, NT, true> : boxqp_cta_kernel<T, NT, false>;

@@ -100,43 +100,6 @@ __device__ __forceinline__ void mux_dmma884(double (&c)[2], double a, double b)
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// Pivot step of the Cholesky factorisation: l = sqrt(a) and r = 1 / l (potf2 scales the column by the reciprocal).  The
-// IEEE sqrt followed by the IEEE reciprocal is a chain of ~160 cycles and ~65 instructions; this one starts from the
-// hardware's reciprocal-square-root seed (MUFU.RSQ64H, ~2^-22), runs two Newton steps and corrects l and r once more:
-// both are within an ulp of the rounded values (the restatement is compared with LAPACK by tolerance, not bit for bit).
-__device__ __forceinline__ void mux_sqrt_rcp(double a, double& l, double& r)
-{
-    // (the seed instruction flushes subnormals: tiny pivots are moved up by 2^200 first, an exact scaling; NaN, +-inf
-    //  and pivots <= 0 produce values nobody uses -- the caller has recorded the breakdown, or LAPACK would return NaN too)
-    const bool tiny = a < 0x1p-900;
-    const double as = tiny ? a * 0x1p200 : a;
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(as));
-    double t = as * y, e = fma(-t, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    t = as * y; e = fma(-t, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    l = as * y;
-    l = fma(fma(-l, l, as), 0.5 * y, l);
-    r = fma(fma(-l, y, 1.0), y, y);
-    l = tiny ? l * 0x1p-100 : l;
-    r = tiny ? r * 0x1p100 : r;
-}
-__device__ __forceinline__ void mux_sqrt_rcp(float a, float& l, float& r)
-{
-    const bool tiny = a < 0x1p-100f;
-    const float as = tiny ? a * 0x1p40f : a;
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(as));
-    const float t = as * y, e = fmaf(-t, y, 1.0f);
-    y = fmaf(0.5f * y, e, y);
-    l = as * y;
-    l = fmaf(fmaf(-l, l, as), 0.5f * y, l);
-    r = fmaf(fmaf(-l, y, 1.0f), y, y);
-    l = tiny ? l * 0x1p-20f : l;
-    r = tiny ? r * 0x1p20f : r;
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // LAPACK ?posvx(FACT='E', UPLO='L') as called at boxcqp.d:194-205 / 310-321, distributed over the 8 lanes of a group:
 // lane gl owns row gl of the system.  Steps as in posvx_small (boxqp_small.cuh): ?poequ / ?laqsy over the free rows,

@@ -473,7 +473,11 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                     T ea[4 * NE], ee[4 * NE];
                     Model::exp_args(pre, xt, ta, ea); Model::exp_args(pre, xt, tb, ea + NE);
                     Model::exp_args(preA, anchor, ta, ea + 2 * NE); Model::exp_args(preA, anchor, tb, ea + 3 * NE);
+#ifdef MIRB200_TPP_EXP_CONV
+                    exp_repro_many_conv<4 * NE>(ea, ee, __activemask());
+#else
                     exp_repro_many<4 * NE>(ea, ee);
+#endif
                     rowFinish(row, A, ta, ya, ee, ee + 2 * NE, true);
                     rowFinish(row + 1, B, tb, yb, ee + NE, ee + 3 * NE, two);
                 };
@@ -545,7 +549,11 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                     const T tb = Model::kHasData ? tp[rowB] : (T)0, yb = Model::kHasData ? YO(rowB) : (T)0;
                     T ea[2 * NE], ee[2 * NE];
                     Model::exp_args(pre, xt, ta, ea); Model::exp_args(pre, xt, tb, ea + NE);
+#ifdef MIRB200_TPP_EXP_CONV
+                    exp_repro_many_conv<2 * NE>(ea, ee, __activemask());
+#else
                     exp_repro_many<2 * NE>(ea, ee);
+#endif
                     rowFinish(row, A, ta, ya, ee, true);
                     rowFinish(row + 1, B, tb, yb, ee + NE, two);
                 };

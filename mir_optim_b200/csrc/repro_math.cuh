@@ -75,12 +75,12 @@ static __device__ __forceinline__ void exp_repro_many(const double* __restrict__
 // number and both exact power-of-two products of the general path reduce to that add.  Anything else (huge arguments,
 // NaN) sends the whole warp through the general path.  20 instead of 33 instructions per exponential.
 template <int K>
-static __device__ __forceinline__ void exp_repro_many_conv(const double* __restrict__ x, double* __restrict__ e)
+static __device__ __forceinline__ void exp_repro_many_conv(const double* __restrict__ x, double* __restrict__ e, unsigned mask = 0xffffffffu)
 {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < K; ++j) ok = ok && (fabs(x[j]) < 700.0);
-    if (__all_sync(0xffffffffu, ok)) {
+    if (__all_sync(mask, ok)) {
         double k[K], r[K], p[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) k[j] = rint(__dmul_rn(x[j], kExpD[0]));
@@ -106,7 +106,7 @@ static __device__ __forceinline__ void exp_repro_many_conv(const double* __restr
     }
 }
 template <int K>
-static __device__ __forceinline__ void exp_repro_many_conv(const float* __restrict__ x, float* __restrict__ e);
+static __device__ __forceinline__ void exp_repro_many_conv(const float* __restrict__ x, float* __restrict__ e, unsigned mask = 0xffffffffu);
 
 template <int K>
 static __device__ __forceinline__ void exp_repro_many(const float* __restrict__ x, float* __restrict__ e)
@@ -138,12 +138,12 @@ static __device__ __forceinline__ void exp_repro_many(const float* __restrict__ 
 }
 
 template <int K>
-static __device__ __forceinline__ void exp_repro_many_conv(const float* __restrict__ x, float* __restrict__ e)
+static __device__ __forceinline__ void exp_repro_many_conv(const float* __restrict__ x, float* __restrict__ e, unsigned mask)
 {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < K; ++j) ok = ok && (fabsf(x[j]) < 80.0f);
-    if (__all_sync(0xffffffffu, ok)) {
+    if (__all_sync(mask, ok)) {
         float k[K], r[K], p[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) k[j] = rintf(__fmul_rn(x[j], kExpS[0]));
@@ -230,5 +230,43 @@ static __device__ __noinline__ double div_ni(double a, double b) { return a / b;
 static __device__ __noinline__ float  div_ni(float a, float b)   { return a / b; }
 static __device__ __noinline__ double sqrt_ni(double a) { return sqrt(a); }
 static __device__ __noinline__ float  sqrt_ni(float a)  { return sqrtf(a); }
+
+// Pivot step of the Cholesky factorisation: l = sqrt(a) and r = 1 / l (potf2 scales the column by the reciprocal).  The
+// IEEE sqrt followed by the IEEE reciprocal is a chain of ~160 cycles and ~65 instructions; this one starts from the
+// hardware's reciprocal-square-root seed (MUFU.RSQ64H, ~2^-22), runs two Newton steps and corrects l and r once more:
+// both are within an ulp of the rounded values (the restatement is compared with LAPACK by tolerance, not bit for bit).
+static __device__ __forceinline__ void mux_sqrt_rcp(double a, double& l, double& r)
+{
+    // (the seed instruction flushes subnormals: tiny pivots are moved up by 2^200 first, an exact scaling; NaN, +-inf
+    //  and pivots <= 0 produce values nobody uses -- the caller has recorded the breakdown, or LAPACK would return NaN too)
+    const bool tiny = a < 0x1p-900;
+    const double as = tiny ? a * 0x1p200 : a;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(as));
+    double t = as * y, e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = as * y; e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    l = as * y;
+    l = fma(fma(-l, l, as), 0.5 * y, l);
+    r = fma(fma(-l, y, 1.0), y, y);
+    l = tiny ? l * 0x1p-100 : l;
+    r = tiny ? r * 0x1p100 : r;
+}
+static __device__ __forceinline__ void mux_sqrt_rcp(float a, float& l, float& r)
+{
+    const bool tiny = a < 0x1p-100f;
+    const float as = tiny ? a * 0x1p40f : a;
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(as));
+    const float t = as * y, e = fmaf(-t, y, 1.0f);
+    y = fmaf(0.5f * y, e, y);
+    l = as * y;
+    l = fmaf(fmaf(-l, l, as), 0.5f * y, l);
+    r = fmaf(fmaf(-l, y, 1.0f), y, y);
+    l = tiny ? l * 0x1p-20f : l;
+    r = tiny ? r * 0x1p20f : r;
+}
+
 
 }  // namespace mirb200
