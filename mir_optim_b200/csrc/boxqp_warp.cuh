@@ -94,8 +94,19 @@ __device__ int posvx_warp(int s, AGet A, WarpQPSmem<T>& sm, int lane, int* equed
     auto Asc = [&](int i, T sci, int c) -> T { const T a = Asym(i, c); return equil ? (sm.sc[c] * sci) * a : a; };
 
     // ---- the lower triangle of the (equilibrated) system, packed, and the scaled right-hand side
-    if (v0) { T* Fr = sm.F + wtri(r0); for (int c = 0; c <= r0; ++c) Fr[c] = Asc(r0, sc0, c); }
-    if (v1) { T* Fr = sm.F + wtri(r1); for (int c = 0; c <= r1; ++c) Fr[c] = Asc(r1, sc1, c); }
+    // (four independent loads in flight per row: the loop is latency-bound on L1 / L2 otherwise)
+    auto fill_row = [&](int r, T scr) {
+        T* Fr = sm.F + wtri(r);
+        int c = 0;
+        for (; c + 3 <= r; c += 4) {
+            const T a0 = A(r, c), a1 = A(r, c + 1), a2 = A(r, c + 2), a3 = A(r, c + 3);
+            if (equil) { Fr[c] = (sm.sc[c] * scr) * a0; Fr[c + 1] = (sm.sc[c + 1] * scr) * a1; Fr[c + 2] = (sm.sc[c + 2] * scr) * a2; Fr[c + 3] = (sm.sc[c + 3] * scr) * a3; }
+            else { Fr[c] = a0; Fr[c + 1] = a1; Fr[c + 2] = a2; Fr[c + 3] = a3; }
+        }
+        for (; c <= r; ++c) Fr[c] = Asc(r, scr, c);
+    };
+    if (v0) fill_row(r0, sc0);
+    if (v1) fill_row(r1, sc1);
     T b0 = v0 ? sm.b[r0] * sc0 : (T)0, b1 = v1 ? sm.b[r1] * sc1 : (T)0;         // dposvx: B := diag(S) B
     __syncwarp();
 
@@ -110,8 +121,23 @@ __device__ int posvx_warp(int s, AGet A, WarpQPSmem<T>& sm, int lane, int* equed
         if (v1 && r1 > j) { T* p = sm.F + wtri(r1) + j; l1 = *p * rinv; *p = l1; sm.col[r1] = l1; }
         if (lane == 0) sm.rdiag[j] = rinv;
         __syncwarp();
-        if (v0 && r0 > j) { T* Fr = sm.F + wtri(r0); for (int k = j + 1; k <= r0; ++k) Fr[k] = fma(-l0, sm.col[k], Fr[k]); }
-        if (v1 && r1 > j) { T* Fr = sm.F + wtri(r1); for (int k = j + 1; k <= r1; ++k) Fr[k] = fma(-l1, sm.col[k], Fr[k]); }
+        {
+            // both rows of the lane in one sweep over k (r0 <= r1: the pivot-column entry is loaded once for the two)
+            T* F0 = sm.F + wtri(r0); T* F1 = sm.F + wtri(r1);
+            const int e0 = (v0 && r0 > j) ? r0 : j, e1 = (v1 && r1 > j) ? r1 : ((v0 && r0 > j) ? r0 : j);
+            int k = j + 1;
+            for (; k + 1 <= e0; k += 2) {
+                const T c0 = sm.col[k], c1 = sm.col[k + 1];
+                const T a0 = F0[k], a1 = F0[k + 1], b0_ = F1[k], b1_ = F1[k + 1];
+                F0[k] = fma(-l0, c0, a0); F0[k + 1] = fma(-l0, c1, a1);
+                if (v1) { F1[k] = fma(-l1, c0, b0_); F1[k + 1] = fma(-l1, c1, b1_); }
+            }
+            for (; k <= e0; ++k) { const T c0 = sm.col[k]; F0[k] = fma(-l0, c0, F0[k]); if (v1) F1[k] = fma(-l1, c0, F1[k]); }
+            if (v1 && r1 > j) {
+                for (; k + 1 <= e1; k += 2) { const T c0 = sm.col[k], c1 = sm.col[k + 1]; const T b0_ = F1[k], b1_ = F1[k + 1]; F1[k] = fma(-l1, c0, b0_); F1[k + 1] = fma(-l1, c1, b1_); }
+                for (; k <= e1; ++k) F1[k] = fma(-l1, sm.col[k], F1[k]);
+            }
+        }
         __syncwarp();
     }
 
@@ -147,10 +173,24 @@ __device__ int posvx_warp(int s, AGet A, WarpQPSmem<T>& sm, int lane, int* equed
         if (v1) sm.sx[r1] = x1;
         __syncwarp();
         T rr0 = b0, rr1 = b1, w0 = t_abs(b0), w1 = t_abs(b1);
-        for (int c = 0; c < s; ++c) {
-            const T xc = sm.sx[c];
-            if (v0) { const T a = Asc(r0, sc0, c); rr0 = fma(-a, xc, rr0); w0 = fma(t_abs(a), t_abs(xc), w0); }
-            if (v1) { const T a = Asc(r1, sc1, c); rr1 = fma(-a, xc, rr1); w1 = fma(t_abs(a), t_abs(xc), w1); }
+        {
+            int c = 0;
+            for (; c + 3 < s; c += 4) {                // eight independent loads in flight
+                T a[4], g[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a[e] = v0 ? Asc(r0, sc0, c + e) : (T)0; g[e] = v1 ? Asc(r1, sc1, c + e) : (T)0; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const T xc = sm.sx[c + e];
+                    rr0 = fma(-a[e], xc, rr0); w0 = fma(t_abs(a[e]), t_abs(xc), w0);
+                    rr1 = fma(-g[e], xc, rr1); w1 = fma(t_abs(g[e]), t_abs(xc), w1);
+                }
+            }
+            for (; c < s; ++c) {
+                const T xc = sm.sx[c];
+                if (v0) { const T a = Asc(r0, sc0, c); rr0 = fma(-a, xc, rr0); w0 = fma(t_abs(a), t_abs(xc), w0); }
+                if (v1) { const T a = Asc(r1, sc1, c); rr1 = fma(-a, xc, rr1); w1 = fma(t_abs(a), t_abs(xc), w1); }
+            }
         }
         T qv = (T)0;                           // dporfs: berr = max_i |r_i| / (|b| + |A||x|)_i with the safe1 / safe2 guard
         if (v0) { const bool big = w0 > safe2; qv = div_ni(big ? t_abs(rr0) : t_abs(rr0) + safe1, big ? w0 : w0 + safe1); }
