@@ -18,7 +18,9 @@ int launch_small_model<REAL>(unsigned model, size_t n, const Num<REAL>::Settings
     // m beyond the largest rows-per-lane instantiation of the lane-group kernel (4 x 32 rows): the thread-per-problem
     // kernel takes any m, whatever the batch size (a single problem is left to the caller: the legacy entry point
     // sends it to the row-parallel large-problem engine instead of one thread)
-    if (use_thread_per_problem(args.batch) || (args.m > 128 && args.batch > 1)) {
+    // (warm-started batches, MIR_MODEL_WARM_START, go to the kernels below: lane-group for m <= 128, general otherwise)
+    const bool warm = (args.flags & MIR_MODEL_WARM_START) != 0;
+    if ((use_thread_per_problem(args.batch) && !(warm && args.m <= 128)) || (args.m > 128 && args.batch > 1 && !warm)) {
         switch (model) {
         case MIR_MODEL_EXPDECAY2:  if (n != 2) return bad_n(2); return launch_tpp<ModelExpDecay2<T, true>, T>(st, args, stream);
         case MIR_MODEL_EXPTAU3:    if (n != 3) return bad_n(3); return launch_tpp<ModelExpTau3<T, true>, T>(st, args, stream);

@@ -107,8 +107,17 @@ template <class Model, class T, bool FD>
 int launch_mux_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
     static const bool lockstep = [] { const char* e = std::getenv("MIRB200_MUX_LOCKSTEP"); return !(e && *e == '0'); }();
-    constexpr int W = sizeof(T) == 8 ? 5 : 10;
-    if (lockstep && args.batch >= (unsigned long long)MUX_SLOTS * W * 2) return launch_mux_w<Model, T, FD, W>(st, args, stream);
+    static const int wEnv = [] { const char* e = std::getenv("MIRB200_MUX_W"); return e ? std::atoi(e) : 0; }();      // experiments: warps per CTA
+    constexpr int W = sizeof(T) == 8 ? 5 : 10;          // as many warps as the shared memory of one SM holds, in ONE CTA
+    constexpr int WH = sizeof(T) == 8 ? 2 : 5;          // two CTAs per SM (they drift out of phase: one in the n-sized phase, one on rows)
+    if (lockstep && args.batch >= (unsigned long long)MUX_SLOTS * W * 2) {
+        // float: two CTAs of 5 warps per SM measured 4.78 M fits/s against 4.50 M for one CTA of 10 (the two drift out of
+        // phase and overlap the latency-bound n-sized phase of one with the FP-heavy row phase of the other); double has 5
+        // warps per SM, which do not split: 2 x 2 warps measured 0.99 M against 1.10 M for one CTA of 5
+        const bool split = wEnv ? (wEnv == WH) : (sizeof(T) == 4);
+        if (split) return launch_mux_w<Model, T, FD, WH>(st, args, stream);
+        return launch_mux_w<Model, T, FD, W>(st, args, stream);
+    }
     return launch_mux_w<Model, T, FD, 1>(st, args, stream);
 }
 template <class Model, class T>

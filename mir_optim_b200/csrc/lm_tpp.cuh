@@ -212,7 +212,7 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
                     for (int i = 0; i < N; ++i) { xt[i] = x[i]; Jy[i] = (T)0; dX[i] = (T)0; }
                     maxAge = st.maxAge ? st.maxAge : (FD ? 2u * N : 3u);                             // LS:945
                     ysel = 0; iterations = 0; fCalls = 0; gCalls = 0; status = mir_ls_maxIterations;
-                    residual = Num<T>::inf(); lambda = warm_lambda<T>(args, prob); mu = (T)1; deltaX_dot = (T)0;
+                    residual = Num<T>::inf(); lambda = (T)0; mu = (T)1; deltaX_dot = (T)0;     // (warm start: the launcher sends those batches to the lane-group / general kernels -- this kernel sits on a register-allocation cliff, the extra load cost 2 %)
                     age = maxAge; needJacobian = false; fConverged = false;
                 }
             }
