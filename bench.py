@@ -211,6 +211,8 @@ def secondary_c4(torch, dist, eng, dev, workloads, sharding, rank, world, m=4_00
     dt, r, stats, x = best
     out = {"value": r.iterations / dt, "unit": "LM iterations/s (whole job)", "m": m, "n": wl.n, "rows_per_rank": hi - lo,
            "solve_s": dt, "iterations": int(r.iterations), "passes": int(stats["passes"]), "passes_per_s": stats["passes"] / dt,
+           "ms_per_pass": dt / max(int(stats["passes"]), 1) * 1e3, "ms_per_accepted_iteration": dt / max(int(r.iterations), 1) * 1e3,
+           "allreduces_per_pass": 0 if world == 1 else 2,
            "status": int(r.status), "fCalls": int(r.fCalls), "gCalls": int(r.gCalls), "residual": float(r.residual),
            "max_rel_err_vs_truth": float(np.max(np.abs(x - wl.truth[0]) / np.abs(wl.truth[0]))),
            "timing": "wall clock around the blocking C-ABI call, device-synchronised, max over ranks, best of 2 after 1 warm-up",

@@ -68,8 +68,8 @@ template <class T> struct MuxSlot {
 };
 template <class T, int W> struct MuxCtaSmem {
     MuxSlot<T> slot[MUX_SLOTS * W];
-    int qn[2], qhead[2], qpub[2];       // row-task queues of the two halves of the pass loop: length, next ticket, warps that have posted
-    unsigned char qtask[2][MUX_SLOTS * W + 4];   // slot of task t; 0 = not posted yet (slots are stored + 1)
+    int qn[2], qhead[2];                // row-task queues of the two halves of the pass loop: length, next task
+    unsigned char qtask[2][MUX_SLOTS * W];
 };
 
 // ---- group (8-lane) collectives, executed by the whole warp; every lane of a group receives the same bits -----------
@@ -622,48 +622,36 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
             }
 
             // =========================================================== row phase: post this slot's request, then pull tasks
-            // A warp starts pulling as soon as it has posted: the queue grows while it is being served (a ticket is valid once
-            // its entry is posted; it is void once every warp has posted and the queue is shorter), so the n-sized phase of a
-            // slow warp overlaps with row work done by the others.  One CTA barrier per half remains (results complete).
+            // (Tried: pulling as soon as a warp has posted, the queue growing while it is served, with fences and a posted-
+            //  warps counter instead of the barrier below -- +3 % at 262,144 fits, but the n-sized phases of the warps end
+            //  together anyway, and compute-sanitizer's racecheck cannot see through flag-based hand-offs.  Not kept.)
             bool evalPending = false;
             if (rf != 0) {
                 my.p[gl] = (rf & MUX_EVAL_TRIAL) ? xt : x;
                 if (rf & MUX_JAC_BROYDEN) my.dX[gl] = dX;
                 if (FD && (rf & MUX_JAC_FRESH)) { my.fxp[gl] = fd_xp; my.fxm[gl] = fd_xm; my.frt[gl] = fd_rt; }
-                if (gl == 0) { my.ddot = deltaX_dot; my.prob = prob; my.flags = rf; my.ysel = ysel; }
+                if (gl == 0) {
+                    my.ddot = deltaX_dot; my.prob = prob; my.flags = rf; my.ysel = ysel;
+                    cta.qtask[half][atomicAdd(&cta.qn[half], 1)] = (unsigned char)myslot;
+                }
                 evalPending = (rf & (MUX_EVAL_INIT | MUX_EVAL_TRIAL)) != 0;
             }
-            __syncwarp();
-            if (rf != 0 && gl == 0) {
-                __threadfence_block();                                               // mailbox before the queue entry
-                const int pos = atomicAdd(&cta.qn[half], 1);
-                *(volatile unsigned char*)&cta.qtask[half][pos] = (unsigned char)(myslot + 1);
+            if constexpr (MUX_WARPS > 1) {
+                if (half == 0) { if (__syncthreads_and(retired)) goto done; }
+                else __syncthreads();
+            } else {
+                if (half == 0 && __all_sync(MUX_FULL, retired)) goto done;
+                __syncwarp();
             }
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                atomicAdd(&cta.qpub[half], 1);
-                if (threadIdx.x == 0) {                                              // the other half's queue is idle during this half
-                    cta.qn[half ^ 1] = 0; cta.qhead[half ^ 1] = 0; cta.qpub[half ^ 1] = 0;
-                    for (int e = 0; e < MUX_SLOTS * MUX_WARPS + 4; ++e) cta.qtask[half ^ 1][e] = 0;
-                }
-            }
+            if (threadIdx.x == 0) { cta.qn[half ^ 1] = 0; cta.qhead[half ^ 1] = 0; }     // the other half's queue is idle now
+            const int nTasks = cta.qn[half];
 #pragma unroll 1
             for (;;) {
-                int s = -1;
-                if (lane == 0) {
-                    const int ticket = atomicAdd(&cta.qhead[half], 1);
-                    if (ticket < MUX_SLOTS * MUX_WARPS) {
-                        for (;;) {
-                            const int v = *(volatile unsigned char*)&cta.qtask[half][ticket];
-                            if (v) { s = v - 1; break; }
-                            if (*(volatile int*)&cta.qpub[half] == MUX_WARPS && *(volatile int*)&cta.qn[half] <= ticket) break;
-                        }
-                    }
-                    __threadfence_block();                                           // queue entry before the mailbox
-                }
-                s = __shfl_sync(MUX_FULL, s, 0);
-                if (s < 0) break;
+                int task = 0;
+                if (lane == 0) task = atomicAdd(&cta.qhead[half], 1);
+                task = __shfl_sync(MUX_FULL, task, 0);
+                if (task >= nTasks) break;
+                const int s = cta.qtask[half][task];
                 MuxSlot<T>& sl = cta.slot[s];
                 const int f = sl.flags;
                 const unsigned long long sprob = sl.prob;
@@ -825,13 +813,7 @@ lm_mux_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args)
                 }
                 __syncwarp();
             }
-            if constexpr (MUX_WARPS > 1) {
-                if (half == 0) { if (__syncthreads_and(retired)) goto done; }
-                else __syncthreads();
-            } else {
-                __syncwarp();
-                if (half == 0 && __all_sync(MUX_FULL, retired)) goto done;
-            }
+            if constexpr (MUX_WARPS > 1) __syncthreads(); else __syncwarp();
             if (evalPending) trial = my.result;
         }
     }

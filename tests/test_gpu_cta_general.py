@@ -90,6 +90,49 @@ def test_gaussmix_batched_with_bounds(eng, oracle_lib):
     assert stats["qp_iterations"] > 0
 
 
+def test_largest_and_smallest_n(eng, oracle_lib):
+    """n = 128 (42 Gaussians + baseline: the shared-memory QP scratch at its maximum) and n = 2 through the general kernel."""
+    from mir_optim_b200 import workloads
+    w = workloads.c4_gaussmix(m=600, K=42, noise=1e-5)
+    B = 5
+    rng = np.random.default_rng(8)
+    x0 = np.tile(w.x0[0], (B, 1)) * rng.uniform(0.999, 1.001, (B, w.n))
+    y = np.tile(w.y, (B, 1))
+    for k in (1, 2):
+        s = eng.settings(np.float64); s.maxIterations = k
+        xg = x0.copy(); rg, _ = eng.optimize_batched(s, ModelId.GAUSSMIX, xg, w.l, w.u, t=w.t, y=y)
+        xo, ro, _ = oracle_batched(oracle_lib, s, ModelId.GAUSSMIX, x0, w.l, w.u, t=w.t, y=y)
+        assert np.array_equal(rg["status"], ro["status"]) and np.array_equal(rg["iterations"], ro["iterations"]) and np.array_equal(rg["gCalls"], ro["gCalls"])
+        assert np.max(rel_err(xg, xo)) < 1e-8, float(np.max(rel_err(xg, xo)))
+    # n = 2, m = 300 (above the lane-group kernel's 128 rows at a small batch)
+    rng = np.random.default_rng(9)
+    t = np.linspace(0, 4, 300); truth = np.stack([rng.uniform(1, 3, 40), rng.uniform(0.5, 1.5, 40)], axis=1)
+    y = truth[:, 0, None] * np.exp(-t[None, :] * truth[:, 1, None]) + 0.01 * rng.normal(size=(40, 300))
+    x0 = truth * rng.uniform(0.8, 1.2, truth.shape)
+    l = np.full(2, -np.inf); u = np.full(2, np.inf)
+    s = eng.settings(np.float64); s.maxIterations = 3
+    xg = x0.copy(); rg, _ = eng.optimize_batched(s, ModelId.EXPDECAY2, xg, l, u, t=t, y=y)
+    xo, ro, _ = oracle_batched(oracle_lib, s, ModelId.EXPDECAY2, x0, l, u, t=t, y=y)
+    assert np.array_equal(rg["status"], ro["status"]) and np.array_equal(rg["fCalls"], ro["fCalls"]) and np.max(rel_err(xg, xo)) < 1e-11
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_fit_spline_few_knots(eng, oracle_lib, n):
+    """Two knots (a line), three (the parabola of the not-a-knot condition) and four (the first general case)."""
+    rng = np.random.default_rng(n)
+    knots = np.cumsum(rng.uniform(0.5, 1.5, n)); P = 25
+    px = np.sort(rng.uniform(knots[0], knots[-1], P)); py = np.cos(px) + 0.02 * rng.normal(size=P)
+    l = np.full(n, -np.inf); u = np.full(n, np.inf)
+    for lam in (0.0, 1e-2):
+        m = P + (1 if lam == 0 else 0)
+        t = np.zeros((1, m)); y = np.zeros((1, m)); t[0, :P] = px; y[0, :P] = py
+        s = eng.settings(np.float64); s.maxIterations = 3
+        vg, rg = eng.fit_spline(s, np.stack([px, py], axis=1), knots, l, u, lam)
+        vo, ro, _ = oracle_batched(oracle_lib, s, ModelId.SPLINE, np.zeros((1, n)), l, u, t=t, y=y, fd_jacobian=True, aux=knots, param=lam)
+        assert (rg["status"], rg["iterations"], rg["fCalls"]) == (ro["status"][0], ro["iterations"][0], ro["fCalls"][0])
+        assert np.max(np.abs(vg - vo[0])) < 1e-8 * max(1.0, np.abs(vo).max())
+
+
 def test_general_kernel_agrees_with_the_specialised_ones():
     """BASELINE configs[1] / configs[2] shapes through lm_cta (MIRB200_BATCH_KERNEL=cta) and through lm_small / lm_mux: same
     statuses and counters on k-step runs, x to rounding."""
