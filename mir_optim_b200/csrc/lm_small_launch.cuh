@@ -79,10 +79,10 @@ int launch_tpp(const typename Num<T>::Settings& st, const SmallBatchArgs& args, 
 }
 
 // Four problems per warp (lm_mux.cuh): n <= 8, m <= 128.  One warp per CTA; the warp's four problems live in its shared memory.
-template <class Model, class T, bool FD, int MUX_WARPS>
+template <class Model, class T, bool FD, int MUX_WARPS, int TEAM0 = MUX_WARPS>
 int launch_mux_w(const typename Num<T>::Settings& st, const SmallBatchArgs& args, cudaStream_t stream)
 {
-    auto kern = lm_mux_kernel<Model, T, FD, MUX_WARPS>;
+    auto kern = lm_mux_kernel<Model, T, FD, MUX_WARPS, TEAM0>;
     const size_t smem = sizeof(MuxCtaSmem<T, MUX_WARPS>);
     static bool attrSet = false;       // (per instantiation)
     if (!attrSet) {
@@ -116,6 +116,9 @@ int launch_mux_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& arg
         // warps per SM, which do not split: 2 x 2 warps measured 0.99 M against 1.10 M for one CTA of 5
         const bool split = wEnv ? (wEnv == WH) : (sizeof(T) == 4);
         if (split) return launch_mux_w<Model, T, FD, WH>(st, args, stream);
+        // double: one CTA of 5 warps in one team.  Two teams of 3 and 2 warps in the CTA (MIRB200_MUX_W=3; named barriers per team)
+        // measured 1.18 M against 1.21 M fits/s back to back: no gain, the teams' queues are too short to balance
+        if (sizeof(T) == 8 && wEnv == 3) return launch_mux_w<Model, T, FD, W, 3>(st, args, stream);
         return launch_mux_w<Model, T, FD, W>(st, args, stream);
     }
     return launch_mux_w<Model, T, FD, 1>(st, args, stream);
