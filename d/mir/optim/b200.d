@@ -26,10 +26,15 @@ enum MirModel : uint
 {
     linear2 = 0, rosenbrock = 1, expDecay2 = 2, expTau3 = 3, sqrtCircle = 4,
     expDecay3 = 5, gauss4 = 6, sumExp = 7, gaussMix = 8,
+    spline = 9,          /// fitSpline's residual (fit_splie.d:58-80): aux = knots, param = lambda
+    userBase = 0x1000,   /// ids returned by mir_b200_model_compile
 }
 
 enum uint mirModelFdJacobian = 1;      /// g == null semantics (least_squares.d:1016-1050)
 enum uint mirModelGridPerProblem = 2;  /// abscissa has batch*m entries
+enum uint mirModelNoTailShortcut = 4;  /// verification only
+enum uint mirModelAuxPerProblem = 8;   /// aux has batch*n entries
+enum uint mirModelWarmStart = 16;      /// results[b].lambda on entry is the initial damping (least_squares.d:141-142, 966)
 
 /// mir_model_desc
 struct MirModelDesc
@@ -38,6 +43,8 @@ struct MirModelDesc
     uint flags;
     const(void)* t;   /// abscissa T[m] or T[batch*m]
     const(void)* y;   /// observations T[batch*m]
+    const(void)* aux; /// model constants T[n] or T[batch*n] (the knots of MirModel.spline); else null
+    double param = 0; /// model constant (lambda of MirModel.spline)
 }
 
 /// mir_batch_stats: device-side work counters summed over a batch
@@ -74,6 +81,22 @@ int mir_optimize_least_squares_batched_dev_d(scope const LeastSquaresSettings!do
 int mir_optimize_least_squares_batched_dev_s(scope const LeastSquaresSettings!float* settings, scope const MirModelDesc* model,
     size_t batch, size_t m, size_t n, float* x, const(float)* l, const(float)* u, size_t boundStride,
     LeastSquaresResult!float* results, MirBatchStats* stats, void* cudaStream);
+
+/// fitSpline (fit_splie.d:26-85) on the GPU: values = the fitted spline values at the knots `x`.
+int mir_fit_spline_d(scope const LeastSquaresSettings!double* settings, size_t points, const(double)* pointsX, const(double)* pointsY,
+    size_t n, const(double)* x, const(double)* l, const(double)* u, double lambda, double* values, LeastSquaresResult!double* result);
+int mir_fit_spline_s(scope const LeastSquaresSettings!float* settings, size_t points, const(float)* pointsX, const(float)* pointsY,
+    size_t n, const(float)* x, const(float)* l, const(float)* u, float lambda, float* values, LeastSquaresResult!float* result); /// ditto
+int mir_fit_spline_batched_d(scope const LeastSquaresSettings!double* settings, size_t batch, size_t points, const(double)* pointsX,
+    const(double)* pointsY, size_t n, const(double)* x, const(double)* l, const(double)* u, double lambda, uint flags,
+    double* values, LeastSquaresResult!double* results, int device); /// ditto
+int mir_fit_spline_batched_s(scope const LeastSquaresSettings!float* settings, size_t batch, size_t points, const(float)* pointsX,
+    const(float)* pointsY, size_t n, const(float)* x, const(float)* l, const(float)* u, float lambda, uint flags,
+    float* values, LeastSquaresResult!float* results, int device); /// ditto
+
+/// Residual models written in CUDA C++ (`template <class REAL> struct UserModel {...}`), compiled at run time (NVRTC).
+int mir_b200_model_compile(const(char)* source, uint* modelId);
+int mir_b200_model_release(uint modelId); /// ditto
 
 /// solveBoxQP (boxcqp.d:85-102) on the GPU; returns BoxQPStatus or -MirB200Error.
 int mir_solve_box_qp_d(scope const BoxQPSettings!double* settings, size_t n, const(double)* P, const(double)* q,
