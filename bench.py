@@ -158,8 +158,16 @@ def secondary_batched(torch, eng, dev, workloads, rank):
             eng.optimize_batched_device(st, wl.model, x, l, u, t=t, y=y, fd_jacobian=True, results=res)
         ms = _timed(torch, step, 2)
         ok = float(np.mean(eng.results_from_bytes(res, dt)["status"] >= 0))
+        # roofline of this config: SURVEY 8d's conservative algorithmic count, 1.6e6 flop per fit (exp = 1 flop), against the
+        # FP64 / FP32 FMA peak measured live; the kernel is lm_mux_kernel (four fits per warp, J^T J on the FP64 tensor pipe)
+        peak = eng.lib.mir_b200_measure_peak_tflops(0 if dt == np.float64 else 2, 3)
+        ach = 1.6e6 * B / (ms * 1e-3) / 1e12
         out[name] = {"value": B / ms * 1e3, "unit": "fits/s per GPU", "batch": B, "m": 128, "n": 8, "jacobian": "finite differences",
-                     "ms": ms, "frac_status_ok": ok}
+                     "ms": ms, "frac_status_ok": ok,
+                     "roofline": {"bound": "fp64_fma" if dt == np.float64 else "fp32_fma", "kernel": "lm_mux_kernel<ModelSumExp<T,8>, T, finite differences>",
+                                  "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
+                                  "algorithmic_flops_per_fit": 1.6e6,
+                                  "hbm_GBps_algorithmic": (1184 if dt == np.float64 else 600) * B / (ms * 1e-3) / 1e9}}
     B, n = 100000, 64
     g = torch.Generator(device=dev); g.manual_seed(5 + rank)
     P = torch.empty(B, n, n, dtype=torch.float64, device=dev)
