@@ -532,6 +532,16 @@ template <class T> size_t cta_smem_bytes(int n, int prepElems)
     return sizeof(T) * ((size_t)10 * n + 8 + prepElems + 1) + CtaQPScratch<T>::bytes(n) + 16;
 }
 
+// The per-CTA scratch (J, J^T J, two residual vectors) is sized by m n: keep the resident wave within a few GB, fewer CTAs
+// if need be (they are persistent and pull problems from a queue, so any grid size solves the batch).
+inline unsigned long long cta_cap_grid(unsigned long long grid, unsigned long long bytesPerCta)
+{
+    const unsigned long long budget = 6ull << 30;
+    const unsigned long long fit = bytesPerCta ? budget / bytesPerCta : grid;
+    if (fit < grid) grid = fit ? fit : 1;
+    return grid;
+}
+
 template <class Model, class T, bool FD>
 int launch_cta_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& args, size_t n, const mir_model_desc& model, cudaStream_t stream)
 {
@@ -550,6 +560,7 @@ int launch_cta_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& arg
     CtaBatchArgs ca;
     ca.b = args; ca.aux = model.aux; ca.param = model.param; ca.n = (unsigned)n; ca.smem_model = 0;
     ca.scratch_stride = (unsigned long long)args.m * n + (unsigned long long)n * n + 2ull * args.m + 4;
+    grid = cta_cap_grid(grid, ca.scratch_stride * sizeof(T));
     T* scratch = nullptr;
     MIRB200_CUDA(cudaMallocAsync((void**)&scratch, sizeof(T) * ca.scratch_stride * grid, stream));
     ca.scratch = scratch;

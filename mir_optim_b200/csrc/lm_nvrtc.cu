@@ -82,8 +82,9 @@ Rtc& rtc()
 struct Compiled { void* module = nullptr; void* fn[2] = {nullptr, nullptr}; };   // fn[FD]
 struct UserModelEntry {
     std::string source;
-    std::unique_ptr<Compiled> byPrecision[2];      // 0 = double, 1 = float
-    std::vector<char> cubinD; std::string namesD[2];   // the double-precision build made at registration, loaded at first use
+    std::mutex mu;                                  // compilation / loading of THIS model (others are not held up)
+    std::map<int, std::unique_ptr<Compiled>> loaded;    // key = device ordinal * 2 + (float ? 1 : 0): a module belongs to one context
+    std::vector<char> cubin[2]; std::string names[2][2];   // compiled code per precision (double: made at registration), kept for other devices
 };
 std::mutex g_mu;
 std::map<uint32_t, std::shared_ptr<UserModelEntry>> g_models;
@@ -140,19 +141,20 @@ int get_compiled(uint32_t id, bool isFloat, Compiled** out)
         if (it == g_models.end()) { set_error("mir_optim_b200: unknown user model id"); return MIR_B200_EINVAL; }
         e = it->second;
     }
-    std::lock_guard<std::mutex> g(g_mu);               // (compilation is serialised: simple and rare)
-    std::unique_ptr<Compiled>& c = e->byPrecision[isFloat ? 1 : 0];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    std::lock_guard<std::mutex> g(e->mu);
+    std::unique_ptr<Compiled>& c = e->loaded[dev * 2 + (isFloat ? 1 : 0)];
     if (!c) {
-        std::vector<char> cubin; std::string names[2];
-        if (!isFloat && !e->cubinD.empty()) { cubin.swap(e->cubinD); names[0] = e->namesD[0]; names[1] = e->namesD[1]; }
-        else { const int rc = compile_source(e->source, isFloat, cubin, names); if (rc) return rc; }
+        const int pi = isFloat ? 1 : 0;
+        if (e->cubin[pi].empty()) { const int rc = compile_source(e->source, isFloat, e->cubin[pi], e->names[pi]); if (rc) return rc; }
         Rtc& r = rtc();
         if (!r.okCu) { set_error("mir_optim_b200: cannot load a compiled model: " + r.whyCu); return MIR_B200_ENODEVICE; }
         auto cc = std::make_unique<Compiled>();
-        int cr = r.cuModuleLoadData(&cc->module, cubin.data());
+        int cr = r.cuModuleLoadData(&cc->module, e->cubin[pi].data());
         if (cr) return cu_fail("cuModuleLoadData (user model)", cr);
         for (int fd = 0; fd < 2; ++fd) {
-            cr = r.cuModuleGetFunction(&cc->fn[fd], cc->module, names[fd].c_str());
+            cr = r.cuModuleGetFunction(&cc->fn[fd], cc->module, e->names[pi][fd].c_str());
             if (cr) return cu_fail("cuModuleGetFunction (user model)", cr);
         }
         c = std::move(cc);
@@ -186,6 +188,7 @@ int launch_user_model(const mir_model_desc& model, size_t n, const typename Num<
     CtaBatchArgs ca;
     ca.b = args; ca.aux = model.aux; ca.param = model.param; ca.n = (unsigned)n; ca.smem_model = 0;
     ca.scratch_stride = (unsigned long long)args.m * n + (unsigned long long)n * n + 2ull * args.m + 4;
+    grid = cta_cap_grid(grid, ca.scratch_stride * sizeof(T));
     T* scratch = nullptr;
     MIRB200_CUDA(cudaMallocAsync((void**)&scratch, sizeof(T) * ca.scratch_stride * grid, stream));
     ca.scratch = scratch;
@@ -213,7 +216,7 @@ int mir_b200_model_compile(const char* source, uint32_t* model_id)
     // validate now (double precision; NVRTC needs no device), so that syntax errors surface at registration
     auto e = std::make_shared<UserModelEntry>();
     e->source = source;
-    const int rc = compile_source(e->source, false, e->cubinD, e->namesD);
+    const int rc = compile_source(e->source, false, e->cubin[0], e->names[0]);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(g_mu);
     *model_id = g_next++;
@@ -226,7 +229,13 @@ int mir_b200_model_release(uint32_t model_id)
     std::lock_guard<std::mutex> g(g_mu);
     auto it = g_models.find(model_id);
     if (it == g_models.end()) return MIR_B200_EINVAL;
-    for (auto& c : it->second->byPrecision) if (c && c->module && rtc().cuModuleUnload) rtc().cuModuleUnload(c->module);
+    // kernels of this model may still be running: modules are unloaded after the devices that hold them are idle
+    int cur = 0; cudaGetDevice(&cur);
+    for (auto& kv : it->second->loaded) {
+        if (!kv.second || !kv.second->module || !rtc().cuModuleUnload) continue;
+        if (cudaSetDevice(kv.first / 2) == cudaSuccess) { cudaDeviceSynchronize(); rtc().cuModuleUnload(kv.second->module); }
+    }
+    cudaSetDevice(cur);
     g_models.erase(it);
     return MIR_B200_OK;
 }
