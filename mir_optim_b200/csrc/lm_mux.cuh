@@ -49,7 +49,7 @@ constexpr unsigned MUX_FULL = 0xffffffffu;
 // as shared memory holds) step through the phases of the pass loop TOGETHER (a CTA barrier after every phase): they
 // share nothing but the instruction cache, which then holds one phase's code for all of them instead of thrashing
 // between five warps in five different phases.
-// (template parameter MUX_WARPS of the kernel)
+// (template parameters MUX_WARPS / TEAM0 of the kernel)
 enum { MUX_EVAL_INIT = 1, MUX_EVAL_TRIAL = 2, MUX_JAC_FRESH = 4, MUX_JAC_BROYDEN = 8 };
 
 // Everything a problem ("slot") keeps between phases, in shared memory of its CTA.
