@@ -228,3 +228,29 @@ def test_fit_spline_float(eng):
     l = np.full(10, -np.inf, np.float32); u = np.full(10, np.inf, np.float32)
     v, r = eng.fit_spline(s, np.stack([PT, PY], axis=1).astype(np.float32), X.astype(np.float32), l, u, 0.0)
     assert r["status"] >= 0 and np.max(np.abs(v - Y0)) < 0.05
+
+
+def test_edge_shapes_of_the_round2_kernels(eng, oracle_lib):
+    """Tiny batches (the single-warp CTA variant of the four-problems-per-warp kernel), one residual row, no rows at all,
+    empty batches -- through the same entry points."""
+    from mir_optim_b200 import workloads
+    # batches of 1, 2, 3, 5 configs[2] problems, and m = 1 (fewer rows than parameters)
+    for B, m in ((1, 128), (2, 128), (3, 100), (5, 1)):
+        wl = workloads.c3_sumexp8(B, m=m, seed=40 + B)
+        s = eng.settings(np.float64); s.maxIterations = 3
+        for fd in (True, False):
+            xg = wl.x0.copy(); rg, _ = eng.optimize_batched(s, wl.model, xg, wl.l, wl.u, t=wl.t, y=wl.y, fd_jacobian=fd)
+            xo, ro, _ = oracle_batched(oracle_lib, s, wl.model, wl.x0, wl.l, wl.u, t=wl.t, y=wl.y, fd_jacobian=fd)
+            assert np.array_equal(rg["status"], ro["status"]) and np.array_equal(rg["iterations"], ro["iterations"]), (B, m, fd)
+            if m > 8:
+                assert np.max(rel_err(xg, xo)) < 1e-8, (B, m, fd)
+    # m = 0: badGuess (LS:930-931), x untouched -- general kernel (n = 6) and the specialised one (n = 8)
+    for n in (6, 8):
+        x = np.ones((3, n)); r, _ = eng.optimize_batched(eng.settings(np.float64), ModelId.SUMEXP, x, np.full(n, -np.inf), np.full(n, np.inf),
+                                                           t=np.zeros(0), y=np.zeros((3, 0)), m=0)
+        assert np.all(r["status"] == S.badGuess) and np.all(x == 1.0)
+    # empty batches
+    r, _ = eng.optimize_batched(eng.settings(np.float64), ModelId.SUMEXP, np.zeros((0, 6)), np.zeros(6), np.ones(6), t=np.zeros(4), y=np.zeros((0, 4)))
+    assert len(r) == 0
+    v, r = eng.fit_spline_batched(eng.settings(np.float64), PT, np.zeros((0, len(PT))), X, np.full(10, -np.inf), np.full(10, np.inf), 0.0)
+    assert v.shape == (0, 10) and len(r) == 0
