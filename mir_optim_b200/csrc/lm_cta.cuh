@@ -9,6 +9,10 @@
 // returning "unsupported" -- fitSpline's residual (fit_splie.d:58-80, n = number of knots), sums of exponentials or
 // Gaussian mixtures with any number of components, and models compiled at run time (NVRTC, lm_nvrtc.cpp).
 //
+// Samples by TMA: when they fit beside the QP scratch (and m is even: 16-byte granularity), each problem's abscissae and
+// observations are staged into shared memory with cp.async.bulk + an mbarrier when the CTA picks the problem up, so the
+// 2n evaluations of a finite-difference Jacobian and every trial evaluation read them from shared memory.
+//
 // Layout.  Persistent CTAs of 128 threads pull problems from an atomic counter.  The n-sized state (x, trial point,
 // bounds, step, J^T y, QP bounds) and the QP scratch live in shared memory; J (row-major m x n, LS:154), J^T J and the two
 // residual vectors live in a per-CTA global scratch that stays in L1/L2.  Rows are dealt to the threads round-robin;
@@ -49,8 +53,36 @@ struct CtaBatchArgs {
     void* scratch;          // per CTA: J (m*n) | JJ (n*n) | vec0 (m) | vec1 (m)
     unsigned long long scratch_stride;   // elements per CTA
     unsigned n;
-    unsigned smem_model;    // bytes of shared memory reserved for Model::prep (two vectors)
+    unsigned stage_m;       // != 0: shared memory holds room for the problem's samples (t, y: 2 * stage_m values) staged by TMA
 };
+
+// ---- TMA bulk copy + mbarrier (as in syrk_dmma.cuh) ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cta_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cta_mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cta_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void cta_mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cta_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cta_mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(cta_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cta_tma_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(cta_smem_u32(dst)), "l"(src), "r"(bytes), "r"(cta_smem_u32(bar)) : "memory");
+}
 
 // ---- deterministic CTA reductions: every thread receives the same bits --------------------------------------------------
 template <class T> __device__ __forceinline__ T cta_sum_all(T v, T* red4)
@@ -232,6 +264,18 @@ lm_cta_kernel(const typename Num<T>::Settings st, const CtaBatchArgs ca)
     CtaQPScratch<T> qw;
     qw.carve(sp, n);
     __shared__ unsigned int s_idx, s_staged;
+    // sample staging area (TMA destination), 16-byte aligned, behind the QP scratch
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int stageM = (int)ca.stage_m;
+    T* const sT = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(reinterpret_cast<unsigned char*>(sp) + CtaQPScratch<T>::bytes(n)) + 15) & ~(uintptr_t)15);
+    T* const sY = sT + stageM;
+    unsigned stageParity = 0;
+    bool tStaged = false;
+    if (stageM) {
+        if (tid == 0) cta_mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
 
     T* const scr = static_cast<T*>(ca.scratch) + (size_t)blockIdx.x * ca.scratch_stride;
     T* const J = scr;                             // m x n row-major (LS:154)
@@ -266,6 +310,21 @@ lm_cta_kernel(const typename Num<T>::Settings st, const CtaBatchArgs ca)
         pb.y = args.y ? static_cast<const T*>(args.y) + prob * m : nullptr;
         pb.aux = ca.aux ? static_cast<const T*>(ca.aux) + ((args.flags & MIR_MODEL_AUX_PER_PROBLEM) ? prob * n : 0) : nullptr;
         pb.param = (T)ca.param;
+        if (stageM && pb.y != nullptr && (reinterpret_cast<uintptr_t>(pb.y) & 15) == 0 && (pb.t == nullptr || (reinterpret_cast<uintptr_t>(pb.t) & 15) == 0)) {
+            const bool perGrid = (args.flags & MIR_MODEL_GRID_PER_PROBLEM) != 0;
+            const bool needT = pb.t != nullptr && (perGrid || !tStaged);
+            const unsigned bytes = (unsigned)(m * sizeof(T));
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the previous problem's generic reads before the async writes
+                cta_mbar_expect_tx(&s_bar, bytes * (needT ? 2u : 1u));
+                cta_tma_g2s(sY, pb.y, bytes, &s_bar);
+                if (needT) cta_tma_g2s(sT, pb.t, bytes, &s_bar);
+            }
+            cta_mbar_wait(&s_bar, stageParity);
+            stageParity ^= 1u;
+            if (pb.t != nullptr) { pb.t = sT; tStaged = true; }
+            pb.y = sY;
+        }
         T* const xg = static_cast<T*>(args.x) + prob * n;
         for (int i = tid; i < n; i += NT) {
             x[i] = xg[i];
@@ -531,6 +590,14 @@ template <class T> size_t cta_smem_bytes(int n, int prepElems)
 {
     return sizeof(T) * ((size_t)10 * n + 8 + prepElems + 1) + CtaQPScratch<T>::bytes(n) + 16;
 }
+// Room for the samples of one problem (t and y, m values each) behind everything else?  m even keeps the TMA copies at
+// 16-byte granularity; the budget leaves at least two CTAs per SM for the small shapes this kernel usually sees.
+template <class T> unsigned cta_stage_m(size_t smemBase, unsigned m)
+{
+    const size_t need = 2 * (size_t)m * sizeof(T) + 32;
+    const bool ok = m > 0 && (m * sizeof(T)) % 16 == 0 && need <= 48 * 1024 && smemBase + need <= 200 * 1024;
+    return ok ? m : 0u;
+}
 
 // The per-CTA scratch (J, J^T J, two residual vectors) is sized by m n: keep the resident wave within a few GB, fewer CTAs
 // if need be (they are persistent and pull problems from a queue, so any grid size solves the batch).
@@ -548,7 +615,9 @@ int launch_cta_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& arg
     if (n > 128) { set_error("mir_optim_b200: the batched path supports n <= 128"); return MIR_B200_EUNSUPPORTED; }
     if (!Model::valid((int)n, (int)args.m)) { set_error("mir_optim_b200: (m, n) not valid for this model"); return MIR_B200_EINVAL; }
     auto kern = lm_cta_kernel<Model, T, FD>;
-    const size_t smem = cta_smem_bytes<T>((int)n, Model::prep_elems((int)n));
+    size_t smem = cta_smem_bytes<T>((int)n, Model::prep_elems((int)n));
+    const unsigned stageM = cta_stage_m<T>(smem, args.m);
+    smem += stageM ? 2 * (size_t)stageM * sizeof(T) + 32 : 0;
     if (smem > 220 * 1024) { set_error("mir_optim_b200: n too large for the shared memory of the general batched kernel"); return MIR_B200_EUNSUPPORTED; }
     MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocksPerSM = 0;
@@ -558,7 +627,7 @@ int launch_cta_fd(const typename Num<T>::Settings& st, const SmallBatchArgs& arg
     unsigned long long grid = (unsigned long long)sm_count() * blocksPerSM;
     if (args.batch < grid) grid = args.batch ? args.batch : 1;
     CtaBatchArgs ca;
-    ca.b = args; ca.aux = model.aux; ca.param = model.param; ca.n = (unsigned)n; ca.smem_model = 0;
+    ca.b = args; ca.aux = model.aux; ca.param = model.param; ca.n = (unsigned)n; ca.stage_m = stageM;
     ca.scratch_stride = (unsigned long long)args.m * n + (unsigned long long)n * n + 2ull * args.m + 4;
     grid = cta_cap_grid(grid, ca.scratch_stride * sizeof(T));
     T* scratch = nullptr;

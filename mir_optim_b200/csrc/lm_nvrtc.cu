@@ -174,7 +174,9 @@ int launch_user_model(const mir_model_desc& model, size_t n, const typename Num<
     if (rc) return rc;
     Rtc& r = rtc();
     void* fn = c->fn[(args.flags & MIR_MODEL_FD_JACOBIAN) ? 1 : 0];      // (a model without jacobian() runs finite differences either way)
-    const size_t smem = cta_smem_bytes<T>((int)n, 1);
+    size_t smem = cta_smem_bytes<T>((int)n, 1);
+    const unsigned stageM = cta_stage_m<T>(smem, args.m);
+    smem += stageM ? 2 * (size_t)stageM * sizeof(T) + 32 : 0;
     if (smem > 220 * 1024) { set_error("mir_optim_b200: n too large for the shared memory of the general batched kernel"); return MIR_B200_EUNSUPPORTED; }
     int cr = r.cuFuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
     if (cr) return cu_fail("cuFuncSetAttribute", cr);
@@ -186,7 +188,7 @@ int launch_user_model(const mir_model_desc& model, size_t n, const typename Num<
     unsigned long long grid = (unsigned long long)sm_count() * blocksPerSM;
     if (args.batch < grid) grid = args.batch ? args.batch : 1;
     CtaBatchArgs ca;
-    ca.b = args; ca.aux = model.aux; ca.param = model.param; ca.n = (unsigned)n; ca.smem_model = 0;
+    ca.b = args; ca.aux = model.aux; ca.param = model.param; ca.n = (unsigned)n; ca.stage_m = stageM;
     ca.scratch_stride = (unsigned long long)args.m * n + (unsigned long long)n * n + 2ull * args.m + 4;
     grid = cta_cap_grid(grid, ca.scratch_stride * sizeof(T));
     T* scratch = nullptr;
