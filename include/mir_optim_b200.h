@@ -424,8 +424,9 @@ int mir_b200_syrk_lower_dev_d(const double* J, size_t rows, size_t n, size_t ldj
  * triangle read), b / x T[batch*n], info int32[batch] (0, or k > 0: factorisation broke down at pivot k; LAPACK's
  * info = n+1 "singular to working precision", which BQ:212/323 accepts, is reported as 0), equed int32[batch]
  * (1 = the ?laqsy equilibration was applied).  variant 0: register-resident solver of the batched LM kernels
- * (n <= 8); 1: shared-memory column loop of the batched BoxQP kernel; 2: blocked solver of the large-problem
- * control kernel (both n <= 128).  Host pointers, synchronous. */
+ * (n <= 8); 1: shared-memory column loop of the CTA-per-QP BoxQP kernel; 2: blocked solver of the large-problem
+ * control kernel (both n <= 128); 3: one warp per system (the warp-per-QP BoxQP kernel, n <= 64); 4: one 8-lane
+ * group per system (the four-problems-per-warp LM kernel, n <= 8).  Host pointers, synchronous. */
 int mir_b200_posvx_batched_d(int variant, size_t batch, size_t n, const double* A, const double* b, double* x,
                              int32_t* info, int32_t* equed, int device);
 int mir_b200_posvx_batched_s(int variant, size_t batch, size_t n, const float* A, const float* b, float* x,

@@ -65,6 +65,11 @@ __device__ __forceinline__ double t_abs(double a)  { return fabs(a); }
 __device__ __forceinline__ float  t_abs(float a)   { return fabsf(a); }
 __device__ __forceinline__ double t_min(double a, double b) { return fmin(a, b); }   // IEEE minNum, as D's fmin
 __device__ __forceinline__ float  t_min(float a, float b)   { return fminf(a, b); }
+// a - b * c in ONE rounding, spelled out: the compiler's own contraction of `a -= b * c` depends on the shape of the
+// surrounding code (measured: the same source line fused in one unrolled copy and split into DMUL + DADD in another),
+// which breaks "same operations, same order => same bits" between two restatements of one algorithm.
+__device__ __forceinline__ double fnma(double b, double c, double a) { return fma(-b, c, a); }
+__device__ __forceinline__ float  fnma(float b, float c, float a)   { return fmaf(-b, c, a); }
 __device__ __forceinline__ double t_max(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ float  t_max(float a, float b)   { return fmaxf(a, b); }
 

@@ -74,8 +74,28 @@ template <class T, int NT> __device__ __forceinline__ T cta_sum_fixed(T v, T* re
     return r;
 }
 
+// The scalar part of the control block (everything before x) as 32-bit words: the one-CTA control kernels copy it into
+// shared memory on entry, work on the copy and write it back on exit.
+template <class T> __host__ __device__ constexpr int large_head_words() { return (int)(offsetof(LargeCtl<T>, x) / 4); }
+template <class T> __device__ __forceinline__ LargeCtl<T>* large_head_load(const LargeCtl<T>* c, unsigned int* buf)
+{
+    static_assert(offsetof(LargeCtl<T>, x) % 4 == 0, "header size");
+    const unsigned int* src = reinterpret_cast<const unsigned int*>(c);
+    for (int i = threadIdx.x; i < large_head_words<T>(); i += blockDim.x) buf[i] = __ldcg(src + i);
+    return reinterpret_cast<LargeCtl<T>*>(buf);       // ONLY the scalar fields may be touched through this pointer
+}
+template <class T> __device__ __forceinline__ void large_head_store(LargeCtl<T>* c, const unsigned int* buf)
+{
+    unsigned int* dst = reinterpret_cast<unsigned int*>(c);
+    for (int i = threadIdx.x; i < large_head_words<T>(); i += blockDim.x) dst[i] = buf[i];
+}
+
 // LS:974-995 guards + choice of the Jacobian work for the pass that follows (LS:996-1015 bookkeeping).
-template <class T> __device__ void large_begin_pass(LargeCtl<T>* c)
+// Runs in ONE thread.  c is the caller's SHARED-MEMORY copy of the control block's scalar header (large_head_load) and
+// x, Jy, l, u its shared copies of the vectors; JJ is the global packed matrix (rare certificate branch only).  The serial
+// walk over the global control block this replaces cost ~15 us per pass: read-modify-write sequences on one cache line,
+// every read an L2 round trip -- the Amdahl term of row-sharded runs.
+template <class T> __device__ void large_begin_pass(LargeCtl<T>* c, const T* x, const T* Jy, const T* l, const T* u, const T* JJ)
 {
     // single thread
     c->jacMode = JAC_NONE; c->doEval = 0; c->skipRest = 0;
@@ -85,38 +105,38 @@ template <class T> __device__ void large_begin_pass(LargeCtl<T>* c)
     if (!(c->lambda <= c->st.maxLambda)) { c->status = mir_ls_furtherImprovement; c->done = 1; return; }   // LS:979-983
     if (c->mu > (T)16 && c->age) { c->needJacobian = 1; c->age = c->maxAge; c->mu = (T)1; }        // LS:984-989
     bool nan = false;                                                                              // LS:990-995
-    for (int i = 0; i < c->n; ++i) nan = nan || !(c->x[i] <= c->x[i]);
+    for (int i = 0; i < c->n; ++i) nan = nan || !(x[i] <= x[i]);
     if (nan) { c->status = mir_ls_numericError; c->done = 1; return; }
     if (!c->needJacobian && c->age == 0 && c->tailShortcut) {
         // inert lambda-overflow tail (proof at tail_is_inert in lm_small.cuh): replay the scalar recurrence only
         T q2 = (T)0, xmin = Num<T>::inf();
-        for (int i = 0; i < c->n; ++i) { q2 += c->Jy[i] * c->Jy[i]; xmin = t_min(xmin, t_abs(c->x[i])); }
+        for (int i = 0; i < c->n; ++i) { q2 += Jy[i] * Jy[i]; xmin = t_min(xmin, t_abs(x[i])); }
         // + maxStep > 0, and BOXCQP must provably return `solved`: no x_i on a bound, or the on-bound certificate
         // (tail_bounds_certificate in lm_small.cuh, same conditions, restated here for run-time n)
         bool ok = c->st.maxStep > (T)0 && xmin > (T)0 && sqrt_ni(q2) < c->lambda * (xmin * (Num<T>::lapack_eps() * (T)0.125));
         bool any = false;
         for (int i = 0; ok && i < c->n; ++i) {
-            ok = (c->l[i] <= c->x[i]) && (c->x[i] <= c->u[i]);
-            any = any || (c->l[i] == c->x[i]) || (c->u[i] == c->x[i]);
+            ok = (l[i] <= x[i]) && (x[i] <= u[i]);
+            any = any || (l[i] == x[i]) || (u[i] == x[i]);
         }
         if (ok && any) {
             const int n = c->n;
             T nu = (T)0, qinf = (T)0;
             for (int i = 0; i < n; ++i) {
                 T row = (T)0;
-                for (int j = 0; j < n; ++j) row += t_abs(c->JJ[trisym(i, j)]);
-                nu = t_max(nu, row); qinf = t_max(qinf, t_abs(c->Jy[i]));
+                for (int j = 0; j < n; ++j) row += t_abs(JJ[trisym(i, j)]);
+                nu = t_max(nu, row); qinf = t_max(qinf, t_abs(Jy[i]));
             }
             ok = c->lambda >= (T)4 * nu;
             const T thr = ((T)8 * nu) * (qinf / c->lambda), dmax = xmin * (Num<T>::lapack_eps() * (T)0.25);
             const T relTol = c->st.qpSettings.relTolerance, absTol = c->st.qpSettings.absTolerance;
             for (int i = 0; ok && i < n; ++i) {
-                const T ql = c->l[i] - c->x[i], qu = c->u[i] - c->x[i];
+                const T ql = l[i] - x[i], qu = u[i] - x[i];
                 const bool onL = ql == (T)0, onU = qu == (T)0;
                 const bool farL = (-ql - dmax) >= (T)2 * (relTol + absTol * t_abs(ql));
                 const bool farU = (qu - dmax) >= (T)2 * (relTol + absTol * t_abs(qu));
                 if (onL && onU) ok = false;
-                else if (onL || onU) ok = (onL ? farU : farL) && (t_abs(c->Jy[i]) >= thr);
+                else if (onL || onU) ok = (onL ? farU : farL) && (t_abs(Jy[i]) >= thr);
                 else ok = farL && farU;
             }
         }
@@ -410,114 +430,154 @@ template <class T> __device__ __forceinline__ void large_reject(LargeCtl<T>* c)
 
 // after the (all-reduced) Jacobian products: LS:1052-1110
 template <class T>
-__global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeCtl<T>* c)
+__global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_mid_kernel(LargeCtl<T>* g)
 {
-    if (c->done) return;
+    if (g->done) return;
+    MIRB200_PHASE(0);
     constexpr int NT = LARGE_CTL_THREADS;
     extern __shared__ __align__(16) unsigned char ctl_smem[];
-    const int n = c->n, tid = threadIdx.x;
+    __shared__ __align__(16) unsigned int s_head[large_head_words<T>() + 2];
+    LargeCtl<T>* c = large_head_load(g, s_head);     // scalars: c (shared copy);  vectors / matrices: g (global)
+    const int tid = threadIdx.x;
+    __shared__ int s_flag;
+    __syncthreads();
+    const int n = c->n;
     CtaQPScratch<T> w;
     w.carve(ctl_smem, n);
     T* vec = reinterpret_cast<T*>(ctl_smem + ((CtaQPScratch<T>::bytes(n) + 15) & ~(size_t)15));
     T* sq = vec; T* sl = vec + n; T* su = vec + 2 * n; T* sx = vec + 3 * n;
     T* sA = vec + 4 * n;                             // packed lower J^T J (undamped), staged once: every P(i, j) below is a shared load
-    __shared__ int s_flag;
     const int np = n * (n + 1) / 2;
+    const bool fresh = c->jacMode != JAC_NONE;
 
-    if (c->jacMode != JAC_NONE) {
-        for (int e = tid; e < np; e += NT) { const T v = c->packed[e]; c->JJ[e] = v; sA[e] = v; }
-    } else {
-        for (int e = tid; e < np; e += NT) sA[e] = c->JJ[e];
+    {
+        // packed J^T J -> shared memory (and, when the Jacobian changed, into the control block's own copy: the host
+        // all-reduces `packed` in place on every pass).  Sixteen loads in flight per thread: one L2 round trip per batch.
+        const T* src = fresh ? g->packed : g->JJ;
+        for (int e0 = 0; e0 < np; e0 += NT * 16) {
+            T v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { const int e = e0 + k * NT + tid; v[k] = (e < np) ? __ldcg(src + e) : (T)0; }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { const int e = e0 + k * NT + tid; if (e < np) { sA[e] = v[k]; if (fresh) g->JJ[e] = v[k]; } }
+        }
     }
-    if (c->jacMode != JAC_NONE) {
-        for (int k = tid; k < n; k += NT) { const T g = c->packed[np + k]; c->Jy[k] = g; sq[k] = g; }
-        __syncthreads();
-        if (tid == 0) {                                                                            // LS:1053-1062
+    // the n-vectors of the step, one parallel round trip: q = J^T y, l - x, u - x  (LS:1074-1077)
+    T xk = (T)0, lk = (T)0, uk = (T)0;
+    for (int k = tid; k < n; k += NT) {
+        const T q = fresh ? __ldcg(g->packed + np + k) : __ldcg(g->Jy + k);
+        if (fresh) g->Jy[k] = q;
+        xk = __ldcg(g->x + k); lk = __ldcg(g->l + k); uk = __ldcg(g->u + k);
+        sq[k] = q; sl[k] = lk - xk; su[k] = uk - xk; sx[k] = (T)0;
+    }
+    __syncthreads();
+    int exitFlag = 0;
+    if (fresh) {
+        if (tid < 32) {                                                                            // LS:1053-1062
             // iamax: first index of max |.|; NaN never wins unless it is element 0 (reference BLAS behaviour)
-            T best = t_abs(sq[0]); T sel = sq[0];
-            for (int k = 1; k < n; ++k) { const T v = t_abs(sq[k]); if (v > best) { best = v; sel = sq[k]; } }
-            int f = 0;
-            if (!(t_abs(sel) > c->st.gradTolerance)) {
-                if (c->age == 0) { c->status = mir_ls_gConverged; c->done = 1; f = 1; }
-                else { c->age = c->maxAge; c->skipRest = 1; f = 1; }
+            T bv = (T)-1; int bi = 0;
+            for (int k = tid; k < n; k += 32) { const T v = t_abs(sq[k]); if (v > bv) { bv = v; bi = k; } }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const T ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
+            if (tid == 0) {
+                const T sel = !(sq[0] == sq[0]) ? sq[0] : sq[bi];
+                int f = 0;
+                if (!(t_abs(sel) > c->st.gradTolerance)) {
+                    if (c->age == 0) { c->status = mir_ls_gConverged; c->done = 1; f = 1; }
+                    else { c->age = c->maxAge; c->skipRest = 1; f = 1; }
+                }
+                s_flag = f;
+            }
+        }
+        __syncthreads();
+        exitFlag = s_flag;
+    }
+    MIRB200_PHASE(1);
+    if (!exitFlag) {
+        if (tid == 0) {
+            if (!(c->lambda >= c->st.minLambda)) {                                                 // LS:1067-1072
+                T dmax = sA[0];
+                for (int i = 1; i < n; ++i) { const T d = sA[tri(i, i)]; if (t_abs(d) > t_abs(dmax)) dmax = d; }
+                c->lambda = (T)(0.001 * (double)dmax);
+                if (!(c->lambda >= c->st.minLambda)) c->lambda = (T)1;
+            }
+        }
+        __syncthreads();
+        const T lambda = c->lambda;
+        const PackedLowerShift<T> P{sA, lambda};                                                  // LS:1078-1079: J^T J + lambda I (i >= j)
+        unsigned iters = 0, solves = 0;
+        MIRB200_PHASE(2);
+        const int qs = cta_boxqp<T, NT, true>(c->st.qpSettings, n, P, sq, sl, su, sx, w, iters, solves);   // LS:1080
+        __syncthreads();
+        MIRB200_PHASE(3);
+        bool nan = false;                                                                          // LS:1087-1092
+        for (int k = tid; k < n; k += NT) nan = nan || !(sx[k] <= sx[k]);
+        const bool anyNan = cta_any<NT>(nan);
+        if (tid == 0) {
+            c->qpSolves += solves; c->qpIters += iters;
+            int f = 0;
+            if (qs != mir_qp_solved || anyNan) { c->status = mir_ls_numericError; c->done = 1; f = 1; }   // LS:1080-1092
             s_flag = f;
         }
         __syncthreads();
-        if (s_flag) return;
-    }
-
-    __syncthreads();
-    if (tid == 0) {
-        if (!(c->lambda >= c->st.minLambda)) {                                                     // LS:1067-1072
-            T dmax = sA[0];
-            for (int i = 1; i < n; ++i) { const T d = sA[tri(i, i)]; if (t_abs(d) > t_abs(dmax)) dmax = d; }
-            c->lambda = (T)(0.001 * (double)dmax);
-            if (!(c->lambda >= c->st.minLambda)) c->lambda = (T)1;
+        if (!s_flag) {
+            bool differs = false;                                                                  // LS:1096-1097, 1108-1110
+            T trial = (T)0;
+            for (int k = tid; k < n; k += NT) {            // (n <= NT: xk, lk, uk are still this thread's element k)
+                const T d = add_rn(add_rn(sx[k], xk), -xk);
+                sx[k] = d; g->dX[k] = d;
+                trial = t_max(t_min(add_rn(d, xk), uk), lk);
+                differs = differs || !((trial == xk) && (signbit(trial) == signbit(xk)));
+            }
+            const bool same = !cta_any<NT>(differs);       // (barrier: sx is complete)
+            if (tid == 0) {
+                T nd = (T)0;                                                                       // LS:1099
+#pragma unroll 8
+                for (int k = 0; k < n; ++k) { const T d = sx[k]; nd += d * d; }
+                c->nd = nd;
+                int take = 0;
+                if (!(sqrt_ni(nd) < c->st.maxStep)) { large_reject(c); c->skipRest = 1; }          // LS:1101-1106
+                else {
+                    take = 1;
+                    ++c->fCalls;                                                                   // LS:1112
+                    c->doEval = same ? 0 : 1;      // f(xt) == y bit for bit when xt == x: the evaluation is skipped, trial = residual
+                    if (same) c->rr = c->residual;
+                }
+                s_flag = take;
+            }
+            __syncthreads();
+            if (s_flag) for (int k = tid; k < n; k += NT) g->xt[k] = trial;
         }
     }
     __syncthreads();
-    const T lambda = c->lambda;
-    for (int k = tid; k < n; k += NT) { sq[k] = c->Jy[k]; sl[k] = c->l[k] - c->x[k]; su[k] = c->u[k] - c->x[k]; sx[k] = (T)0; }   // LS:1074-1077
-    __syncthreads();
-    auto P = [&](int i, int j) -> T { const T v = sA[tri(i, j)]; return i == j ? v + lambda : v; };   // LS:1078-1079 (i >= j)
-    unsigned iters = 0, solves = 0;
-    const int qs = cta_boxqp<T, NT, true>(c->st.qpSettings, n, P, sq, sl, su, sx, w, iters, solves);   // LS:1080
-    __syncthreads();
-    bool nan = false;                                                                              // LS:1087-1092
-    for (int k = tid; k < n; k += NT) nan = nan || !(sx[k] <= sx[k]);
-    const bool anyNan = cta_any<NT>(nan);
-    if (tid == 0) {
-        c->qpSolves += solves; c->qpIters += iters;
-        int f = 0;
-        if (qs != mir_qp_solved || anyNan) { c->status = mir_ls_numericError; c->done = 1; f = 1; }   // LS:1080-1092
-        s_flag = f;
-    }
-    __syncthreads();
-    if (s_flag) return;
-
-    for (int k = tid; k < n; k += NT) {                                                            // LS:1096-1097
-        const T xk = c->x[k];
-        const T d = add_rn(add_rn(sx[k], xk), -xk);
-        sx[k] = d; c->dX[k] = d;
-    }
-    __syncthreads();
-    bool differs = false;                                                                          // LS:1108-1110 (all threads)
-    for (int k = tid; k < n; k += NT) {
-        const T xk = c->x[k];
-        const T v = t_max(t_min(add_rn(sx[k], xk), c->u[k]), c->l[k]);
-        sq[k] = v;                                   // (sq is free now) trial point, published below if the step is taken
-        differs = differs || !((v == xk) && (signbit(v) == signbit(xk)));
-    }
-    const bool same = !cta_any<NT>(differs);
-    if (tid == 0) {
-        T nd = (T)0;                                                                               // LS:1099
-        for (int k = 0; k < n; ++k) nd += sx[k] * sx[k];
-        c->nd = nd;
-        int take = 0;
-        if (!(sqrt_ni(nd) < c->st.maxStep)) { large_reject(c); c->skipRest = 1; }                  // LS:1101-1106
-        else {
-            take = 1;
-            ++c->fCalls;                                                                           // LS:1112
-            c->doEval = same ? 0 : 1;      // f(xt) == y bit for bit when xt == x: the evaluation is skipped, trial = residual
-            if (same) c->rr = c->residual;
-        }
-        s_flag = take;
-    }
-    __syncthreads();
-    if (s_flag) for (int k = tid; k < n; k += NT) c->xt[k] = sq[k];
+    large_head_store(g, s_head);
+    MIRB200_PHASE(4);
+    MIRB200_PHASE_DUMP();
 }
 
 // after the (all-reduced) trial residual: LS:1117-1175, then the guards of the next pass
 template <class T>
-__global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(LargeCtl<T>* c)
+__global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(LargeCtl<T>* g)
 {
-    if (c->done) return;
-    constexpr int NT = LARGE_CTL_THREADS;
-    __shared__ T sdx[LARGE_NMAX], sjy[LARGE_NMAX], red[NT / 32];
+    if (g->done) return;
+    __shared__ T sxv[LARGE_NMAX], sdx[LARGE_NMAX], sjy[LARGE_NMAX], slo[LARGE_NMAX], sup[LARGE_NMAX];
+    __shared__ __align__(16) unsigned int s_head[large_head_words<T>() + 2];
     __shared__ int s_go;
-    const int n = c->n, tid = threadIdx.x;
+    LargeCtl<T>* c = large_head_load(g, s_head);     // scalars: c (shared copy);  vectors / matrices: g (global)
+    const int tid = threadIdx.x;
+    const int n = g->n;
 
+    // one parallel round trip for every n-vector the serial parts below walk over
+    T xtk = (T)0;
+    if (tid < n) {
+        sxv[tid] = __ldcg(g->x + tid); sdx[tid] = __ldcg(g->dX + tid); sjy[tid] = __ldcg(g->Jy + tid);
+        slo[tid] = __ldcg(g->l + tid); sup[tid] = __ldcg(g->u + tid); xtk = __ldcg(g->xt + tid);
+    }
+    __syncthreads();
     if (c->initPhase) {                                                                            // LS:953-971
         if (tid == 0) {
             c->initPhase = 0;
@@ -525,8 +585,10 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
             c->fConverged = (c->residual <= c->st.maxGoodResidual) ? 1 : 0;
             c->needJacobian = 1; c->age = c->maxAge; c->lambda = (T)0; c->iterations = 0; c->mu = (T)1;
             c->status = mir_ls_maxIterations; c->deltaX_dot = (T)0;
-            large_begin_pass(c);
+            large_begin_pass(c, sxv, sjy, slo, sup, g->JJ);
         }
+        __syncthreads();
+        large_head_store(g, s_head);
         return;
     }
 
@@ -546,14 +608,22 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
     __syncthreads();
     if (s_go) {
         // accepted: LS:1132-1139
-        for (int k = tid; k < n; k += NT) { c->x[k] = c->xt[k]; sdx[k] = c->dX[k]; }
-        __syncthreads();
+        if (tid < n) { g->x[tid] = xtk; sxv[tid] = xtk; }
         // symv(Lower, 1, JJ, deltaX, 2, Jy) with the undamped JJ, then pred = -Jy . deltaX          LS:1141-1142
-        for (int i = tid; i < n; i += NT) {
+        // (row i of the packed matrix, j ascending; 32 loads in flight per thread)
+        if (tid < n) {
+            const int i = tid;
             T acc = (T)0;
-            for (int j = 0; j < n; ++j) acc += c->JJ[trisym(i, j)] * sdx[j];
-            const T v = acc + (T)2 * c->Jy[i];
-            c->Jy[i] = v; sjy[i] = v;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                T v[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { const int j = j0 + k; v[k] = (j < n) ? __ldcg(g->JJ + trisym(i, j)) : (T)0; }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { const int j = j0 + k; if (j < n) acc += v[k] * sdx[j]; }
+            }
+            const T v = acc + (T)2 * sjy[i];
+            g->Jy[i] = v;
+            sjy[i] = v;
         }
         __syncthreads();
         if (tid == 0) {
@@ -563,6 +633,7 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
             c->fConverged = (c->residual <= c->st.maxGoodResidual) ? 1 : 0;
             c->deltaX_dot = c->nd;
             T pred = (T)0;
+#pragma unroll 8
             for (int k = 0; k < n; ++k) pred += sjy[k] * sdx[k];
             pred = -pred;
             if (!(pred > (T)0)) { c->status = mir_ls_furtherImprovement; c->done = 1; }            // LS:1144-1148
@@ -572,12 +643,14 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
                 else if (rho >= c->st.goodStepQuality) c->lambda = t_max(c->st.lambdaDecrease * c->lambda * c->mu, c->st.minLambda);   // LS:1158-1161
                 // LS:1164: !(sqrt(dd) > absTol && nrm2(x) > sqrt(dd) * relTol)
                 T xmax = (T)0;
-                for (int k = 0; k < n; ++k) xmax = t_max(xmax, t_abs(c->x[k]));
+#pragma unroll 8
+                for (int k = 0; k < n; ++k) xmax = t_max(xmax, t_abs(sxv[k]));
                 T xn = (T)0;
                 if (xmax > (T)0) {
                     const T inv = rcp_ni(xmax);
                     T ss = (T)0;
-                    for (int k = 0; k < n; ++k) { const T v = c->x[k] * inv; ss += v * v; }
+#pragma unroll 8
+                    for (int k = 0; k < n; ++k) { const T v = sxv[k] * inv; ss += v * v; }
                     xn = xmax * sqrt_ni(ss);
                 }
                 const T sd = sqrt_ni(c->deltaX_dot);
@@ -591,9 +664,10 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
     __syncthreads();
     if (tid == 0 && !c->done) {
         if (!(c->iterations < c->st.maxIterations)) { c->status = mir_ls_maxIterations; c->done = 1; }   // LS:1175
-        else large_begin_pass(c);
+        else large_begin_pass(c, sxv, sjy, slo, sup, g->JJ);
     }
-    (void)red;
+    __syncthreads();
+    large_head_store(g, s_head);
 }
 
 }  // namespace mirb200

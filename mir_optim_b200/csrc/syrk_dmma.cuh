@@ -330,6 +330,13 @@ __global__ void __launch_bounds__(256) syrk_reduce_kernel(const double* __restri
         const double* p = partial + (size_t)i * SYRK_NPAD + j;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int c = 0;
+        for (; c + 16 <= nparts; c += 16) {            // sixteen loads in flight (one L2 round trip), added in the order of the loop below
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = __ldcg(p + (size_t)(c + k) * (SYRK_NPAD * SYRK_NPAD));
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) { s0 += v[k]; s1 += v[k + 1]; s2 += v[k + 2]; s3 += v[k + 3]; }
+        }
         for (; c + 4 <= nparts; c += 4) {
             s0 += p[(size_t)(c + 0) * (SYRK_NPAD * SYRK_NPAD)];
             s1 += p[(size_t)(c + 1) * (SYRK_NPAD * SYRK_NPAD)];

@@ -241,7 +241,7 @@ def test_posvx_device_restatements_against_lapack(eng, oracle_lib, dtype, n):
     rng = np.random.default_rng(1000 + n)
     batch = 64 if n <= 17 else 12
     eps = 2.2e-16 if dtype == np.float64 else 1.2e-7
-    variants = ([0] if n <= 8 else []) + [1, 2]
+    variants = ([0, 4] if n <= 8 else []) + [1, 2] + ([3] if n <= 64 else [])      # 3: one warp per system, 4: 8-lane groups (round 2)
     worst = {}
     for kind in ("well", "scaled", "near", "indef"):
         if n == 1 and kind in ("near", "indef"):
