@@ -290,6 +290,22 @@ def test_posvx_device_restatements_against_lapack(eng, oracle_lib, dtype, n):
     report(f"posvx_n{n}_{np.dtype(dtype).name}", **{f"{k}_v{v}": e for (k, v), e in worst.items()})
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [9, 64, 100, 127, 128])
+def test_posvx_blocked_and_column_loop_give_the_same_bits(eng, dtype, n):
+    """The register-tiled blocked LDL^T + warp-level solves of the large-problem control kernel (variant 2) perform, for
+    every entry, the operations of the column loop (variant 1) in the same order: the solutions must agree bit for bit,
+    equilibrated or not.  (Round 2 found the compiler contracting the same `a -= b * c` into one DFMA in one unrolled copy
+    and DMUL + DADD in another; every LDL^T restatement now spells its fused multiply-subtract out.)"""
+    rng = np.random.default_rng(77 + n)
+    for kind in ("well", "scaled"):
+        A, b = _spd_batch(rng, 8, n, dtype, kind)
+        x1, i1, e1 = eng.posvx_batched(A, b, 1)
+        x2, i2, e2 = eng.posvx_batched(A, b, 2)
+        assert np.array_equal(i1, i2) and np.array_equal(e1, e2), kind
+        assert np.array_equal(x1.view(np.uint64 if dtype == np.float64 else np.uint32), x2.view(np.uint64 if dtype == np.float64 else np.uint32)), (kind, float(np.max(np.abs(x1 - x2))))
+
+
 def test_posvx_refinement_is_exercised(eng, oracle_lib):
     """A system whose first solve is NOT yet at backward error eps (cond ~ 1e10, no equilibration possible: unit diagonal):
     the <= 5 ?porfs sweeps must bring the device solution to the same x as LAPACK's to ~cond * eps."""
