@@ -578,7 +578,9 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
         slo[tid] = __ldcg(g->l + tid); sup[tid] = __ldcg(g->u + tid); xtk = __ldcg(g->xt + tid);
     }
     __syncthreads();
-    if (c->initPhase) {                                                                            // LS:953-971
+    const int initPhase = c->initPhase;
+    __syncthreads();                                 // (every thread has read the flag before thread 0 clears it in the shared copy)
+    if (initPhase) {                                                                               // LS:953-971
         if (tid == 0) {
             c->initPhase = 0;
             c->residual = c->rr; c->ysel ^= 1; c->fCalls = 1;
@@ -662,9 +664,11 @@ __global__ void __launch_bounds__(LARGE_CTL_THREADS) large_ctl_post_kernel(Large
         }
     }
     __syncthreads();
-    if (tid == 0 && !c->done) {
-        if (!(c->iterations < c->st.maxIterations)) { c->status = mir_ls_maxIterations; c->done = 1; }   // LS:1175
-        else large_begin_pass(c, sxv, sjy, slo, sup, g->JJ);
+    if (tid == 0) {
+        if (!*(volatile int*)&c->done) {             // (volatile: not hoisted above the branch into the other threads)
+            if (!(c->iterations < c->st.maxIterations)) { c->status = mir_ls_maxIterations; c->done = 1; }   // LS:1175
+            else large_begin_pass(c, sxv, sjy, slo, sup, g->JJ);
+        }
     }
     __syncthreads();
     large_head_store(g, s_head);
