@@ -322,8 +322,12 @@ __global__ void __launch_bounds__(256) large_jac_kernel(const JacArgs<T> a)
             if (FD) syo_[tid] = ok ? a.yobs[row] : (T)0;
         }
         __syncthreads();
-        for (int w = tid; w < LARGE_TILE * items; w += NT) {
-            const int r = w / items, item = w - r * items;
+        // lane = row of the tile, warp = item (stride NT / 32): the item -- and with it every branch and parameter load
+        // of jac_item -- is uniform over a warp, the shared-memory stores of a warp walk one column of the tile (pitch
+        // ldj + 1: conflict-free), and no division by the run-time item count is needed
+        static_assert(LARGE_TILE == 32, "lane = tile row");
+        for (int item = tid >> 5; item < items; item += NT / 32) {
+            const int r = tid & 31;
             if (row0 + r >= a.rows) continue;
             if (!FD) {
                 ParamView<T> pv{sp, saux, -1, (T)0, (T)0};
