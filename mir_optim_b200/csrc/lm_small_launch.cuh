@@ -41,7 +41,8 @@ int launch_tpp_cfg(const typename Num<T>::Settings& st, const SmallBatchArgs& ar
     int blocksPerSM = 0;
     const size_t mPad = ((size_t)args.m + 1) & ~(size_t)1;
     // shared abscissa (+ observations) (+ the accepted steps of the v-list)
-    const size_t smem = sizeof(T) * (mPad + (YOS ? (size_t)args.m * TPP_THREADS : 0) + (VL ? (size_t)TPP_VLN * Model::N * TPP_THREADS : 0));
+    const size_t smem = sizeof(T) * (mPad + (YOS ? (size_t)args.m * TPP_THREADS : 0) + (VL ? (size_t)TPP_VLN * Model::N * TPP_THREADS : 0)
+                                     + ((VL && TPP_CPA) ? (size_t)TppPrefetch<Model>::ELEMS * TPP_THREADS : 0));
     if (smem > 200 * 1024) { set_error("mir_optim_b200: m too large for the thread-per-problem kernel"); return MIR_B200_EUNSUPPORTED; }
     if (smem > 48 * 1024) MIRB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MIRB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, TPP_THREADS, smem));
@@ -49,7 +50,7 @@ int launch_tpp_cfg(const typename Num<T>::Settings& st, const SmallBatchArgs& ar
     unsigned long long blocksWanted = (args.batch + TPP_THREADS - 1) / TPP_THREADS;
     unsigned long long grid = (unsigned long long)sm_count() * blocksPerSM;
     if (blocksWanted < grid) grid = blocksWanted ? blocksWanted : 1;
-    const size_t perThread = (size_t)args.m * TppSlab<Model::N, YOS, VL>::ELEMS;
+    const size_t perThread = (size_t)args.m * TppSlabOf<Model, YOS, VL>::ELEMS;
     T* slab = nullptr;
     MIRB200_CUDA(cudaMallocAsync((void**)&slab, sizeof(T) * (perThread ? perThread : 1) * TPP_THREADS * grid, stream));
     kern<<<(unsigned)grid, TPP_THREADS, smem, stream>>>(st, args, slab);
