@@ -71,6 +71,11 @@ constexpr bool TPP_AE = MIRB200_TPP_ANCHOR_EXP != 0;
 #define MIRB200_TPP_CPASYNC 0
 #endif
 constexpr bool TPP_CPA = MIRB200_TPP_CPASYNC != 0;
+// v-list scheme: slab loads bypass the L1 (ld.global.cg) so that it keeps the bounds, settings and spill lines
+#ifndef MIRB200_TPP_SLAB_CG
+#define MIRB200_TPP_SLAB_CG 0
+#endif
+template <class T> __device__ __forceinline__ T tpp_slab_ld(const T* p) { if constexpr (MIRB200_TPP_SLAB_CG != 0) return __ldcg(p); else return *p; }
 // fields per row of the cp.async prefetch: f_old, v_0, v_1 (+ the anchor exps)
 constexpr int TPP_CPA_DEPTH = MIRB200_TPP_CPASYNC;
 template <class Model> struct TppPrefetch { static constexpr int F = 3 + (TPP_AE ? Model::NE : 0); static constexpr int ELEMS = (TPP_CPA_DEPTH + 1) * 2 * F; };
@@ -458,9 +463,9 @@ lm_tpp_kernel(const typename Num<T>::Settings st, const SmallBatchArgs args, T* 
 #pragma unroll
                         for (int q = 0; q < NE; ++q) in.ea[q] = (kB && on) ? pE[((size_t)q * m + row) * NT] : (T)0;
                     }
-                    in.fo = (kB && on) ? fold[row * NT] : (T)0;
-                    in.v0 = (kB && k > 0 && on) ? pV[row * NT] : (T)0;
-                    in.v1 = (kB && k > 1 && on) ? pV[(size_t)m * NT + row * NT] : (T)0;
+                    in.fo = (kB && on) ? tpp_slab_ld(fold + row * NT) : (T)0;
+                    in.v0 = (kB && k > 0 && on) ? tpp_slab_ld(pV + row * NT) : (T)0;
+                    in.v1 = (kB && k > 1 && on) ? tpp_slab_ld(pV + (size_t)m * NT + row * NT) : (T)0;
                 };
                 // Branch-free: every lane runs the Broyden arithmetic (selects pick the result, loads and stores are
                 // predicated).  eT / eA: the exps of this row at the trial point and at the anchor.
